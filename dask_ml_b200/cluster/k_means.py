@@ -1,0 +1,511 @@
+"""KMeans with the dask_ml.cluster.KMeans API, executed by the B200 engine.
+
+Mirrors dask_ml/cluster/k_means.py (reference @ 0310a90):
+  KMeans                      :26-233     k_means            :236-275
+  k_init                      :291-369    init_pp            :372-384
+  init_random                 :387-393    init_scalable      :396-463
+  evaluate_cost/_sample_points :466-491   _kmeans_single_lloyd :499-569
+The host loop keeps the reference's control flow (including its quirks Q1-Q6);
+all arithmetic over X runs in the CUDA kernels behind include/bkm_b200.h.
+"""
+import logging
+from numbers import Integral
+
+import numpy as np
+import torch
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.utils.validation import check_is_fitted
+
+from ..chunked import ChunkedArray, as_chunked, is_dask_array, is_dask_dataframe, _is_torch
+from ..engine import Comm, CudaBackend, DeviceData, _NP_TO_TORCH
+from ..utils import _timed, _timer, check_array
+
+logger = logging.getLogger(__name__)
+
+# Replaced by tests that exercise the host loop on CPU with a checker backend.
+_BACKEND_FACTORY = CudaBackend
+
+
+def _get_backend():
+    return _BACKEND_FACTORY()
+
+
+# ---------------------------------------------------------------------------------------
+# input handling
+# ---------------------------------------------------------------------------------------
+_NONFINITE_MSG = "Input contains NaN, infinity or a value too large for dtype('float64')."
+
+
+def _to_blocks(X):
+    """ndarray / torch tensor / ChunkedArray / dask array -> list of 2-D blocks."""
+    if isinstance(X, ChunkedArray):
+        return X.blocks
+    if is_dask_array(X):
+        return as_chunked(X).blocks
+    return [X]
+
+
+def _block_np_dtype(b):
+    from ..chunked import block_dtype
+
+    return block_dtype(b)
+
+
+def _to_device_data(X, backend=None, comm=None, check_finite=True):
+    """Validated array-like -> DeviceData (rows resident on the device)."""
+    if isinstance(X, DeviceData):
+        return X
+    backend = backend or _get_backend()
+    blocks = _to_blocks(X)
+    dt = _block_np_dtype(blocks[0])
+    if dt == np.dtype("int32") or dt == np.dtype("float16"):
+        dt = np.dtype("float32")            # k_means.py:171-172
+    elif dt == np.dtype("int64"):
+        dt = np.dtype("float64")            # k_means.py:173-174
+    elif dt not in (np.dtype("float32"), np.dtype("float64")):
+        dt = np.dtype("float64")
+    tdt = _NP_TO_TORCH[dt]
+    chunks = [backend.to_device(b, tdt) for b in blocks]
+    data = DeviceData(chunks, backend, comm)
+    if check_finite:
+        flag = backend.check_finite(chunks)
+        comm_ = data.comm
+        flag_f = flag.to(torch.float64)
+        comm_.allreduce_sum_(flag_f)
+        if float(flag_f.item()) != 0.0:
+            raise ValueError(_NONFINITE_MSG)    # k_means.py:179-185
+    return data
+
+
+class KMeans(TransformerMixin, BaseEstimator):
+    """Scalable KMeans for clustering (API of dask_ml.cluster.KMeans, k_means.py:26-152).
+
+    Parameters
+    ----------
+    n_clusters : int, default 8
+    init : {'k-means||', 'k-means++', 'random'} or ndarray of shape (n_clusters, n_features)
+    oversampling_factor : int, default 2
+        Oversampling factor ``l`` of k-means|| (Bahmani et al. 2012, Alg. 2).
+    max_iter : int
+        Maximum number of EM (Lloyd) iterations.
+    init_max_iter : int
+        Number of k-means|| rounds; default ``round(log(cost))``.
+    tol : float
+        Convergence threshold on ``||C - C'||_F^2`` (raw, as in the reference, k_means.py:555-559).
+    random_state : int, RandomState or None
+    precompute_distances, copy_x, n_jobs, algorithm :
+        Accepted for scikit-learn signature compatibility and ignored, as in the reference
+        (k_means.py:148-152).
+
+    Attributes
+    ----------
+    cluster_centers_ : np.ndarray (n_clusters, n_features), dtype of X
+    labels_ : ChunkedArray (n_samples,) int32 — device-resident, ``.compute()`` gives numpy
+    inertia_ : np.float64
+    n_iter_ : int
+    """
+
+    def __init__(
+        self,
+        n_clusters=8,
+        init="k-means||",
+        oversampling_factor=2,
+        max_iter=300,
+        tol=0.0001,
+        precompute_distances="auto",
+        random_state=None,
+        copy_x=True,
+        n_jobs=1,
+        algorithm="full",
+        init_max_iter=None,
+    ):
+        self.n_clusters = n_clusters
+        self.init = init
+        self.oversampling_factor = oversampling_factor
+        self.random_state = random_state
+        self.max_iter = max_iter
+        self.init_max_iter = init_max_iter
+        self.algorithm = algorithm
+        self.tol = tol
+        self.precompute_distances = precompute_distances
+        self.n_jobs = n_jobs
+        self.copy_x = copy_x
+
+    @_timed(_logger=logger)
+    def _check_array(self, X):
+        """Validation of k_means.py:154-186, ending with X resident on the device."""
+        try:
+            import pandas as pd
+
+            if isinstance(X, pd.DataFrame):
+                X = X.values
+        except ImportError:  # pragma: no cover
+            pass
+        if is_dask_dataframe(X):
+            raise TypeError("Cannot fit on dask.dataframe due to unknown partition lengths.")
+        if isinstance(X, DeviceData):
+            return X
+        X = check_array(
+            X,
+            accept_dask_dataframe=False,
+            accept_unknown_chunks=False,
+            accept_sparse=False,
+        )
+        return _to_device_data(X)
+
+    def fit(self, X, y=None):
+        X = self._check_array(X)
+        labels, centroids, inertia, n_iter = k_means(
+            X,
+            self.n_clusters,
+            oversampling_factor=self.oversampling_factor,
+            random_state=self.random_state,
+            init=self.init,
+            return_n_iter=True,
+            max_iter=self.max_iter,
+            init_max_iter=self.init_max_iter,
+            tol=self.tol,
+        )
+        self.cluster_centers_ = centroids
+        self.labels_ = labels
+        self.inertia_ = inertia
+        self.n_iter_ = n_iter
+        self.n_features_in_ = centroids.shape[1]
+        return self
+
+    def transform(self, X, y=None):
+        check_is_fitted(self, "cluster_centers_")
+        X = self._check_array(X)
+        from ..metrics.pairwise import euclidean_distances
+
+        return euclidean_distances(X, self.cluster_centers_)
+
+    def predict(self, X):
+        """Index of the closest centre for every row (k_means.py:212-233); int32 labels."""
+        check_is_fitted(self, "cluster_centers_")
+        X = self._check_array(X)
+        from ..metrics.pairwise import pairwise_distances_argmin_min
+
+        labels = pairwise_distances_argmin_min(X, self.cluster_centers_)[0].astype(np.int32)
+        return labels
+
+
+def k_means(
+    X,
+    n_clusters,
+    init="k-means||",
+    precompute_distances="auto",
+    n_init=1,
+    max_iter=300,
+    verbose=False,
+    tol=1e-4,
+    random_state=None,
+    copy_x=True,
+    n_jobs=-1,
+    algorithm="full",
+    return_n_iter=False,
+    oversampling_factor=2,
+    init_max_iter=None,
+):
+    """K-means clustering, functional form (k_means.py:236-275)."""
+    labels, inertia, centers, n_iter = _kmeans_single_lloyd(
+        X,
+        n_clusters,
+        max_iter=max_iter,
+        init=init,
+        verbose=verbose,
+        tol=tol,
+        random_state=random_state,
+        oversampling_factor=oversampling_factor,
+        init_max_iter=init_max_iter,
+    )
+    if return_n_iter:
+        return labels, centers, inertia, n_iter
+    else:
+        return labels, centers, inertia
+
+
+# ---------------------------------------------------------------------------------------
+# Initialisation
+# ---------------------------------------------------------------------------------------
+def _as_random_state(random_state, comm):
+    """Same stream on every rank: ints/None seed a RandomState (None -> rank 0 draws the seed)."""
+    if isinstance(random_state, np.random.RandomState):
+        return random_state
+    if random_state is None:
+        seed = comm.bcast_obj(int(np.random.randint(0, 2 ** 31 - 1)))
+        return np.random.RandomState(seed)
+    return np.random.RandomState(int(random_state))
+
+
+def k_init(
+    X,
+    n_clusters,
+    init="k-means||",
+    random_state=None,
+    max_iter=None,
+    oversampling_factor=2,
+):
+    """Choose the initial centres (k_means.py:291-369).  Returns np.ndarray (k, d)."""
+    n_features = X.d if isinstance(X, DeviceData) else X.shape[1]
+    if isinstance(init, np.ndarray):
+        K, P = init.shape
+
+        if K != n_clusters:
+            msg = "Number of centers in provided 'init' ({}) does not match 'n_clusters' ({})"
+            raise ValueError(msg.format(K, n_clusters))
+
+        if P != n_features:
+            msg = "Number of features in the provided 'init' ({}) do not match the number of features in 'X'"
+            raise ValueError(msg.format(P, n_features))
+
+        return init
+
+    elif not isinstance(init, str):
+        raise TypeError("'init' must be an array or str, got {}".format(type(init)))
+
+    valid = {"k-means||", "k-means++", "random"}
+    if init not in valid:
+        raise ValueError("'init' must be one of {}, got {}".format(valid, init))
+
+    X = _to_device_data(X, check_finite=False)
+    if isinstance(random_state, Integral) or random_state is None:
+        random_state = _as_random_state(random_state, X.comm)
+
+    if init == "k-means||":
+        return init_scalable(X, n_clusters, random_state, max_iter, oversampling_factor)
+    elif init == "k-means++":
+        return init_pp(X, n_clusters, random_state)
+    else:
+        return init_random(X, n_clusters, random_state)
+
+
+def init_pp(X, n_clusters, random_state):
+    """k-means++ through scikit-learn on the host, like the reference (k_means.py:372-384):
+    the whole dataset is brought into host memory (single-process only)."""
+    from sklearn.cluster import kmeans_plusplus
+
+    if X.comm.world != 1:
+        raise NotImplementedError("init='k-means++' loads all of X on one host; use 'k-means||' when distributed")
+    logger.info("Initializing with k-means++")
+    Xh = X.to_host()
+    with _timer("initialization of %2d centers" % n_clusters, _logger=logger):
+        centers, _ = kmeans_plusplus(Xh, n_clusters, random_state=random_state)
+    return centers
+
+
+@_timed(_logger=logger)
+def init_random(X, n_clusters, random_state):
+    """Centres = randomly chosen rows (k_means.py:387-393)."""
+    logger.info("Initializing randomly")
+    idx = sorted(random_state.randint(0, X.n_global, size=n_clusters))
+    return X.global_rows(idx)
+
+
+class _AssignPass(object):
+    """One E-step-only sweep over all local chunks against a fixed set of centres."""
+
+    def __init__(self, X):
+        self.X = X
+        self.be = X.backend
+
+    def run(self, centers64, want_labels=False, want_min=False, squared=True):
+        be, X = self.be, self.X
+        k = centers64.shape[0]
+        C = torch.as_tensor(np.ascontiguousarray(centers64, dtype=np.float64)).to(be.device)
+        pack = be.pack_centers(C, X.dtype)
+        acc = be.zeros((1,), torch.float64)
+        labels, mins = [], []
+        for x in X.chunks:
+            n = x.shape[0]
+            lab = be.empty((n,), torch.int32) if want_labels else None
+            mn = be.empty((n,), X.dtype) if want_min else None
+            be.assign_chunk(x, pack, k, lab, mn, squared, acc)
+            labels.append(lab)
+            mins.append(mn)
+        X.comm.allreduce_sum_(acc)
+        return labels, mins, acc
+
+
+@_timed(_logger=logger)
+def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_factor=2):
+    """k-means|| (Bahmani et al. 2012, Alg. 2) following k_means.py:396-463.
+
+    Each round is one distance sweep on the device (``bkm_assign_chunk``: min d^2 per row and
+    the cost phi) followed by the Bernoulli draw kernel (``bkm_sample_chunk``).  The reference
+    draws U with dask's per-chunk RandomState (k_means.py:487); here U comes from a counter-based
+    Philox stream keyed by a per-round seed and the global row index, so a run is reproducible
+    for a given ``random_state`` independent of chunking and of the number of GPUs.
+    """
+    logger.info("Initializing with k-means||")
+    be, comm = X.backend, X.comm
+    rs = random_state if isinstance(random_state, np.random.RandomState) else _as_random_state(random_state, comm)
+    sweep = _AssignPass(X)
+
+    # Step 1: first centre = global row 0 (k_means.py:406-408)
+    idx = 0
+    centers = X.global_rows([idx])
+    c_idx = {idx}
+
+    # Step 2: initial cost (k_means.py:411-420)
+    _, _, cost_t = sweep.run(centers.astype(np.float64), squared=True)
+    cost = float(cost_t.item())
+    if cost == 0:
+        n_iter = 0
+    else:
+        n_iter = int(np.round(np.log(cost)))
+    if max_iter is not None:
+        n_iter = min(max_iter, n_iter)
+
+    # Steps 3-6: oversampling rounds (k_means.py:423-435)
+    for i in range(n_iter):
+        with _timer("init iteration %2d/%2d , %2d centers" % (i + 1, n_iter, len(c_idx)), _logger=logger):
+            seed = int(rs.randint(0, 2 ** 31 - 1)) | (int(rs.randint(0, 2 ** 31 - 1)) << 32)
+            _, mins, phi_t = sweep.run(centers.astype(np.float64), want_min=True, squared=True)
+            phi = float(phi_t.item())
+            new_idxs = set()
+            if phi > 0:
+                cap = max(1024, 8 * int(oversampling_factor) + 1024)
+                while True:
+                    picked = be.empty((cap,), torch.int64)
+                    n_picked = be.zeros((1,), torch.int32)
+                    off = X.row_offset
+                    for x, mn in zip(X.chunks, mins):
+                        be.sample_chunk(mn, oversampling_factor / phi, seed, off, picked, n_picked)
+                        off += int(x.shape[0])
+                    m = int(n_picked.item())
+                    if m <= cap:
+                        break
+                    cap = m
+                local = picked[:m].cpu().numpy().tolist()
+                for part in comm.allgather_obj(local):
+                    new_idxs |= set(int(v) for v in part)
+            c_idx |= new_idxs
+        # sorted, like the reference (k_means.py:432-435)
+        centers = X.global_rows(sorted(c_idx))
+
+    if len(centers) < n_clusters:
+        logger.warning("Found fewer than %d clusters in init.", n_clusters)
+        # supplement with random rows (k_means.py:445-455)
+        need = n_clusters - len(centers)
+        locs = sorted(rs.choice(np.arange(0, X.n_global), size=need, replace=False))
+        extra = X.global_rows(locs)
+        return np.vstack([centers, extra])
+    else:
+        # Steps 7, 8 without weights (k_means.py:457-463): the few candidates are reduced to k
+        # centres by an in-memory KMeans on the host, as the reference does with scikit-learn.
+        from sklearn.cluster import KMeans as _SKKMeans
+
+        rng2 = int(rs.randint(0, 2 ** 32 - 1, dtype=np.int64))
+        km = _SKKMeans(n_clusters, random_state=rng2, n_init=10)
+        km.fit(centers)
+        return km.cluster_centers_
+
+
+def evaluate_cost(X, centers):
+    """phi_X(C) = sum_i min_j ||x_i - c_j||^2 (k_means.py:466-469); X is DeviceData."""
+    X = _to_device_data(X, check_finite=False)
+    _, _, acc = _AssignPass(X).run(np.asarray(centers, dtype=np.float64), squared=True)
+    return float(acc.item())
+
+
+# ---------------------------------------------------------------------------------------
+# EM steps
+# ---------------------------------------------------------------------------------------
+class LloydState(object):
+    """Device-resident state of the Lloyd loop; ``step()`` is one full iteration:
+    fused E+M kernel per chunk -> one all-reduce -> centre update + shift (k_means.py:522-555).
+    No host synchronisation happens inside ``step()``."""
+
+    def __init__(self, X, centers):
+        be = X.backend
+        self.X, self.be = X, be
+        k, d = centers.shape
+        self.k, self.d = int(k), int(d)
+        self.C = torch.as_tensor(np.ascontiguousarray(centers, dtype=np.float64)).to(be.device)
+        self.C_new = be.empty((k, d), torch.float64)
+        # one buffer so that the per-iteration collective is a single all-reduce
+        self.red = be.zeros((k * d + k + 1,), torch.float64)
+        self.sums = self.red[: k * d]
+        self.counts_f = self.red[k * d: k * d + k]
+        self.inertia = self.red[k * d + k:]
+        self.counts = be.zeros((k,), torch.int64)
+        self.shift = be.zeros((1,), torch.float64)
+        self.labels = [be.empty((int(x.shape[0]),), torch.int32) for x in X.chunks]
+        self.pack = None
+
+    def step(self):
+        be, X, k = self.be, self.X, self.k
+        self.pack = be.pack_centers(self.C, X.dtype, out=self.pack)
+        self.red.zero_()
+        self.counts.zero_()
+        for x, lab in zip(X.chunks, self.labels):
+            be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts, self.inertia)
+        if X.comm.world > 1:
+            self.counts_f.copy_(self.counts)
+            X.comm.allreduce_sum_(self.red)
+            self.counts.copy_(self.counts_f.round())
+        be.finalize(self.sums, self.counts, self.C, self.C_new, self.shift)
+
+    def accept(self):
+        self.C, self.C_new = self.C_new, self.C
+
+    def relabel(self, squared):
+        """E-step only against the current centres; returns the summed min distance tensor."""
+        be, X, k = self.be, self.X, self.k
+        self.pack = be.pack_centers(self.C, X.dtype, out=self.pack)
+        acc = be.zeros((1,), torch.float64)
+        for x, lab in zip(X.chunks, self.labels):
+            be.assign_chunk(x, self.pack, k, lab, None, squared, acc)
+        X.comm.allreduce_sum_(acc)
+        return acc
+
+
+def _kmeans_single_lloyd(
+    X,
+    n_clusters,
+    max_iter=300,
+    init="k-means||",
+    verbose=False,
+    x_squared_norms=None,
+    random_state=None,
+    tol=1e-4,
+    precompute_distances=True,
+    oversampling_factor=2,
+    init_max_iter=None,
+):
+    """Lloyd iterations with the reference's exact control flow (k_means.py:499-569)."""
+    X = _to_device_data(X)
+    centers = k_init(
+        X,
+        n_clusters,
+        init=init,
+        oversampling_factor=oversampling_factor,
+        random_state=random_state,
+        max_iter=init_max_iter,
+    )
+    dt = X.np_dtype
+    st = LloydState(X, np.asarray(centers))
+    shift = None
+    i = -1
+    for i in range(max_iter):
+        with _timer("Lloyd loop %2d." % i, _logger=logger):
+            st.step()
+            shift = float(st.shift.item())       # the one host sync per iteration (k_means.py:552)
+            logger.info("Shift: %0.4f", shift)
+            if shift < tol:
+                break                            # Q3: break BEFORE centers = new_centers
+            st.accept()
+
+    if shift is None:
+        raise ValueError("max_iter must be at least 1, got %r" % (max_iter,))
+
+    if shift > 1e-7:
+        # Q4: re-label against the current centres with the default (non-squared) metric
+        inertia = float(st.relabel(squared=False).item())
+    else:
+        inertia = float(st.inertia.item())
+
+    labels = ChunkedArray(st.labels)
+    centers = st.C.cpu().numpy().astype(dt)
+    return labels, np.float64(inertia), centers, i + 1

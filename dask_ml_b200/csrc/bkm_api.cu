@@ -1,0 +1,203 @@
+// bkm_api.cu — the extern "C" boundary declared in include/bkm_b200.h: argument validation,
+// kernel-family dispatch, workspace carving.  No allocation, no synchronisation, no throws.
+#include "bkm_common.cuh"
+#include <math.h>
+
+namespace bkm {
+int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s);
+int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
+                    double* shift, int k, int d, cudaStream_t s);
+int launch_sample(const void* d2, long long n, int dtype, double eop, uint64_t seed, uint64_t off,
+                  long long* picked, long long cap, int* n_picked, cudaStream_t s);
+int launch_transform(const void* X, long long n, int d, long long ldx, int dtype,
+                     const void* pack, int k, void* out, int sm_count, cudaStream_t s);
+int launch_check_finite(const void* X, long long n, int d, long long ldx, int dtype, int* flag,
+                        int sm_count, cudaStream_t s);
+
+static int g_sm_count[64];
+static int sm_count_of_current(int* out) {
+  int dev = 0;
+  BKM_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return BKM_EINVAL;
+  if (g_sm_count[dev] == 0) {
+    int v = 0;
+    BKM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    g_sm_count[dev] = v;
+  }
+  *out = g_sm_count[dev];
+  return 0;
+}
+
+// Near-tie margin coefficient: a row is re-evaluated in float64 when
+//   second_best - best <= tau * (||x||^2 + max_j ||c_j||^2).
+// fp32 dot products of length d carry a rounding error of about sqrt(d)*2^-24 relative to
+// sum|x_i c_i| <= (||x||^2+||c||^2)/2; both distances and the -2 factor give the constant.
+static float tau_for(int d, int dtype, int flags, int family) {
+  if (dtype != BKM_F32 || (flags & BKM_FLAG_NO_RECHECK)) return 0.f;
+  float eps = family == 1 ? 1.0f / 1048576.0f   /* 3xTF32: ~2^-20 */
+                          : 1.0f / 16777216.0f; /* fp32 FMA chain: 2^-24 */
+  return 8.0f * (sqrtf((float)d) + 2.0f) * eps;
+}
+
+static int chunk_common(const void* X, long long n, int d, long long ldx, int x_dtype,
+                        const void* pack, int k, int* labels, void* min_out, int squared,
+                        bool mstep, double* sums, long long* counts, double* dist_sum,
+                        void* ws, size_t ws_bytes, int flags, cudaStream_t s) {
+  if (n < 0 || d <= 0 || k <= 0 || ldx < d) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!pack || !ws) return BKM_EINVAL;
+  if (mstep && (!sums || !counts)) return BKM_EINVAL;
+  if (n == 0) return 0;
+  if (!X) return BKM_EINVAL;
+  WsLayout W = ws_layout(d, k, x_dtype);
+  if (ws_bytes < W.total) return BKM_EWORKSPACE;
+  int sm = 0;
+  int rc = sm_count_of_current(&sm);
+  if (rc) return rc;
+
+  ChunkArgs a;
+  a.X = X; a.n = n; a.d = d; a.ldx = ldx;
+  a.pack = (const unsigned char*)pack;
+  a.L = pack_layout(k, d, x_dtype);
+  a.k = k; a.labels = labels; a.min_out = min_out; a.squared = squared;
+  a.psum = (unsigned char*)ws + W.off_psum;
+  a.pcnt = (int*)((unsigned char*)ws + W.off_pcnt);
+  a.pin = (double*)((unsigned char*)ws + W.off_pin);
+
+  int family = bkm_kernel_family(d, k, x_dtype, flags);
+  if (family < 0) return family;
+  a.tau = tau_for(d, x_dtype, flags, family);
+  int grid = 0;
+  if (family == 1) rc = launch_tc(a, mstep, sm, &grid, s);
+  else rc = launch_simt(a, mstep, x_dtype, sm, &grid, s);
+  if (rc) return rc;
+  return launch_reduce_partials(a, grid, mstep, x_dtype, sums, counts, dist_sum, s);
+}
+
+}  // namespace bkm
+
+using namespace bkm;
+
+extern "C" {
+
+int bkm_version(void) { return BKM_VERSION; }
+
+const char* bkm_error_string(int code) {
+  switch (code) {
+    case BKM_OK: return "ok";
+    case BKM_EINVAL: return "invalid argument";
+    case BKM_EDTYPE: return "unsupported dtype";
+    case BKM_EUNSUPPORTED: return "shape not supported by any kernel";
+    case BKM_EWORKSPACE: return "workspace too small";
+    case BKM_EALIGN: return "pointer alignment";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}
+
+int bkm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  int v = 0;
+  BKM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  if (sm_count) *sm_count = v;
+  BKM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device));
+  if (cc_major) *cc_major = v;
+  BKM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device));
+  if (cc_minor) *cc_minor = v;
+  return 0;
+}
+
+int bkm_kernel_family(int d, int k, int x_dtype, int flags) {
+  if (d <= 0 || k <= 0) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  bool tc = tc_supported(d, k, x_dtype);
+  if (flags & BKM_FLAG_FORCE_SIMT) return 0;
+  if (flags & BKM_FLAG_FORCE_TC) return tc ? 1 : BKM_EUNSUPPORTED;
+  return tc ? 1 : 0;
+}
+
+int bkm_centers_pack_bytes(int k, int d, int x_dtype, size_t* out) {
+  if (k <= 0 || d <= 0 || !out) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  *out = pack_layout(k, d, x_dtype).total;
+  return 0;
+}
+
+int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype, void* pack,
+                     size_t pack_bytes, void* stream) {
+  if (!centers64 || !pack || k <= 0 || d <= 0) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (pack_bytes < pack_layout(k, d, x_dtype).total) return BKM_EWORKSPACE;
+  if ((uintptr_t)pack & 255) return BKM_EALIGN;
+  return launch_pack(centers64, k, d, x_dtype, pack, (cudaStream_t)stream);
+}
+
+int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out) {
+  (void)n;
+  if (k <= 0 || d <= 0 || !out) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  *out = ws_layout(d, k, x_dtype).total;
+  return 0;
+}
+
+int bkm_lloyd_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, const void* pack,
+                    int k, int32_t* labels, void* min_d2, double* sums, int64_t* counts,
+                    double* inertia, void* workspace, size_t workspace_bytes, int flags,
+                    void* stream) {
+  return chunk_common(X, n, d, ldx, x_dtype, pack, k, labels, min_d2, 1, true, sums,
+                      (long long*)counts, inertia, workspace, workspace_bytes, flags,
+                      (cudaStream_t)stream);
+}
+
+int bkm_assign_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, const void* pack,
+                     int k, int32_t* labels, void* min_dist, int squared, double* dist_sum,
+                     void* workspace, size_t workspace_bytes, int flags, void* stream) {
+  return chunk_common(X, n, d, ldx, x_dtype, pack, k, labels, min_dist, squared ? 1 : 0, false,
+                      nullptr, nullptr, dist_sum, workspace, workspace_bytes, flags,
+                      (cudaStream_t)stream);
+}
+
+int bkm_sample_chunk(const void* min_d2, int64_t n, int x_dtype, double ell_over_phi,
+                     uint64_t seed, uint64_t row_offset, int64_t* picked, int64_t cap,
+                     int* n_picked, void* stream) {
+  if (n < 0 || cap < 0 || !n_picked || (cap > 0 && !picked)) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (n > 0 && !min_d2) return BKM_EINVAL;
+  return launch_sample(min_d2, n, x_dtype, ell_over_phi, seed, row_offset, (long long*)picked, cap,
+                       n_picked, (cudaStream_t)stream);
+}
+
+int bkm_transform_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
+                        const void* pack, int k, void* out, void* stream) {
+  if (n < 0 || d <= 0 || k <= 0 || ldx < d || !pack) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (n == 0) return 0;
+  if (!X || !out) return BKM_EINVAL;
+  int sm = 0;
+  int rc = sm_count_of_current(&sm);
+  if (rc) return rc;
+  return launch_transform(X, n, d, ldx, x_dtype, pack, k, out, sm, (cudaStream_t)stream);
+}
+
+int bkm_finalize(const double* sums, const int64_t* counts, const double* centers_old,
+                 double* centers_new, double* shift, int k, int d, void* stream) {
+  if (!sums || !counts || !centers_old || !centers_new || !shift || k <= 0 || d <= 0) return BKM_EINVAL;
+  return launch_finalize(sums, (const long long*)counts, centers_old, centers_new, shift, k, d,
+                         (cudaStream_t)stream);
+}
+
+int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, int* flag,
+                     void* stream) {
+  if (n < 0 || d <= 0 || ldx < d || !flag) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (n == 0) return 0;
+  if (!X) return BKM_EINVAL;
+  int sm = 0;
+  int rc = sm_count_of_current(&sm);
+  if (rc) return rc;
+  return launch_check_finite(X, n, d, ldx, x_dtype, flag, sm, (cudaStream_t)stream);
+}
+
+int64_t bkm_launch_count(void) { return (int64_t)g_launches; }
+
+}  // extern "C"

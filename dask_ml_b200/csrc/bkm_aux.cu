@@ -1,0 +1,341 @@
+// bkm_aux.cu — small kernels around the fused chunk kernel: centre packing, deterministic
+// reduction of per-CTA partials, centre update + shift, k-means|| sampling, transform, NaN scan.
+#include "bkm_common.cuh"
+#include <math_constants.h>
+
+namespace bkm {
+
+long long g_launches = 0;
+
+// ---------------------------------------------------------------------------------------
+// pack_centers: float64 centres [k][d] -> every layout the kernels read (see PackLayout).
+//   cT   [k][d4]  x-dtype, zero padded          cnT  [k] x-dtype   ||c||^2 (computed in f64)
+//   c64  [k][d]   float64 copy                  cn64 [k] float64
+//   bhi  [kp][dk] fp32: tf32-rounded (-2 c)     blo  [kp][dk] fp32: (-2 c) - bhi
+//   cn32 [kp]     fp32 ||c||^2, +inf for padded centres
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void pack_centers_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L) {
+  const int k = L.k, d = L.d;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  double* c64 = reinterpret_cast<double*>(pack + L.off_c64);
+  for (int i = tid; i < k * d; i += nth) c64[i] = C[i];
+  if (L.dtype == BKM_F32) {
+    float* cT = reinterpret_cast<float*>(pack + L.off_cT);
+    for (int i = tid; i < k * L.d4; i += nth) {
+      int r = i / L.d4, c = i - r * L.d4;
+      cT[i] = c < d ? (float)C[(size_t)r * d + c] : 0.f;
+    }
+    float* bhi = reinterpret_cast<float*>(pack + L.off_bhi);
+    float* blo = reinterpret_cast<float*>(pack + L.off_blo);
+    for (int i = tid; i < L.kp * L.dk; i += nth) {
+      int r = i / L.dk, c = i - r * L.dk;
+      float hi = 0.f, lo = 0.f;
+      if (r < k && c < d) {
+        double v = -2.0 * C[(size_t)r * d + c];
+        hi = to_tf32_rna((float)v);
+        lo = (float)(v - (double)hi);
+      }
+      bhi[i] = hi; blo[i] = lo;
+    }
+  } else {
+    double* cT = reinterpret_cast<double*>(pack + L.off_cT);
+    for (int i = tid; i < k * L.d4; i += nth) {
+      int r = i / L.d4, c = i - r * L.d4;
+      cT[i] = c < d ? C[(size_t)r * d + c] : 0.0;
+    }
+  }
+}
+
+// one warp per centre: ||c||^2 in float64, then block 0 computes the max.
+__global__ void pack_norms_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L) {
+  const int k = L.k, d = L.d;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  double* cn64 = reinterpret_cast<double*>(pack + L.off_cn64);
+  float* cn32 = reinterpret_cast<float*>(pack + L.off_cn32);
+  for (int j = wid; j < L.kp; j += nw) {
+    double s = 0.0;
+    if (j < k) for (int i = lane; i < d; i += 32) { double v = C[(size_t)j * d + i]; s = fma(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (j < k) {
+        cn64[j] = s;
+        if (L.dtype == BKM_F32) reinterpret_cast<float*>(pack + L.off_cnT)[j] = (float)s;
+        else reinterpret_cast<double*>(pack + L.off_cnT)[j] = s;
+      }
+      if (L.dtype == BKM_F32) cn32[j] = j < k ? (float)s : CUDART_INF_F;
+    }
+  }
+}
+
+__global__ void pack_header_kernel(unsigned char* pack, PackLayout L) {
+  const double* cn64 = reinterpret_cast<const double*>(pack + L.off_cn64);
+  __shared__ double sm[32];
+  double m = 0.0;
+  for (int j = threadIdx.x; j < L.k; j += blockDim.x) m = fmax(m, cn64[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sm[w]);
+    PackHeader* h = reinterpret_cast<PackHeader*>(pack);
+    h->k = L.k; h->d = L.d; h->dtype = L.dtype; h->pad = 0; h->cn_max = m;
+  }
+}
+
+int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s) {
+  PackLayout L = pack_layout(k, d, dtype);
+  int nb = (L.kp * L.dk + 255) / 256; if (nb > 296) nb = 296; if (nb < 1) nb = 1;
+  pack_centers_kernel<<<nb, 256, 0, s>>>(C, (unsigned char*)pack, L);
+  int nb2 = (L.kp + 7) / 8; if (nb2 > 148) nb2 = 148;
+  pack_norms_kernel<<<nb2, 256, 0, s>>>(C, (unsigned char*)pack, L);
+  pack_header_kernel<<<1, 256, 0, s>>>((unsigned char*)pack, L);
+  note_launch(3);
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// reduce_partials: fold the per-CTA partials of one chunk into the float64 accumulators in a
+// FIXED order (CTA 0,1,2,...), so a chunk's contribution is bit-reproducible run to run.
+// ---------------------------------------------------------------------------------------
+template <typename PS>
+__global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* __restrict__ pcnt,
+                                       const double* __restrict__ pin, int grid, int sum_parts,
+                                       int kd, int k, bool mstep,
+                                       double* sums, long long* counts, double* dist_sum) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  if (mstep) {
+    for (int i = tid; i < kd; i += nth) {
+      double s = 0.0;
+      for (int g = 0; g < sum_parts; ++g) s += (double)psum[(size_t)g * kd + i];
+      sums[i] += s;
+    }
+    for (int i = tid; i < k; i += nth) {
+      long long c = 0;
+      for (int g = 0; g < grid; ++g) c += pcnt[(size_t)g * k + i];
+      counts[i] += c;
+    }
+  }
+  if (tid == 0 && dist_sum) {
+    double s = 0.0;
+    for (int g = 0; g < grid; ++g) s += pin[g];
+    *dist_sum += s;
+  }
+}
+
+int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
+                           double* sums, long long* counts, double* dist_sum, cudaStream_t s) {
+  // grid < 0 : the kernel ran in GLOBAL mode (sums accumulated by atomics into slot 0)
+  int sum_parts = grid < 0 ? 1 : grid;
+  if (grid < 0) grid = -grid;
+  const int kd = a.k * a.d;
+  int nb = (kd + 255) / 256; if (nb > 148) nb = 148; if (nb < 1) nb = 1;
+  if (dtype == BKM_F32)
+    reduce_partials_kernel<float><<<nb, 256, 0, s>>>((const float*)a.psum, a.pcnt, a.pin, grid, sum_parts,
+                                                     kd, a.k, mstep, sums, counts, dist_sum);
+  else
+    reduce_partials_kernel<double><<<nb, 256, 0, s>>>((const double*)a.psum, a.pcnt, a.pin, grid, sum_parts,
+                                                      kd, a.k, mstep, sums, counts, dist_sum);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: C' = sums / max(counts,1) ; shift = ||C - C'||_F^2   (k_means.py:548-555)
+// single CTA, fixed-order reduction -> deterministic shift.
+// ---------------------------------------------------------------------------------------
+__global__ void finalize_kernel(const double* __restrict__ sums, const long long* __restrict__ counts,
+                                const double* __restrict__ Cold, double* __restrict__ Cnew,
+                                double* shift, int k, int d) {
+  __shared__ double sm[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
+    int j = i / d;
+    long long c = counts[j];
+    double cn = sums[i] / (double)(c > 1 ? c : 1);
+    Cnew[i] = cn;
+    double df = Cold[i] - cn;
+    acc = fma(df, df, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
+    *shift = s;
+  }
+}
+
+int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
+                    double* shift, int k, int d, cudaStream_t s) {
+  finalize_kernel<<<1, 1024, 0, s>>>(sums, counts, Cold, Cnew, shift, k, d);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// k-means|| Bernoulli sampling (k_means.py:472-491).  U_i = Philox4x32-10 keyed by `seed`,
+// counter = global row index; the first 32-bit output word / 2^32 is the uniform draw.
+// The same generator is restated in numpy under tests/ so the draw sequence is pinned.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t philox_first_word(uint64_t seed, uint64_t ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+template <typename T>
+__global__ void sample_kernel(const T* __restrict__ d2, long long n, double ell_over_phi,
+                              uint64_t seed, uint64_t row_offset, long long* picked, long long cap,
+                              int* n_picked) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double p = ell_over_phi * (double)d2[i];
+    double u = (double)philox_first_word(seed, row_offset + (uint64_t)i) * (1.0 / 4294967296.0);
+    if (p > u) {
+      int slot = atomicAdd(n_picked, 1);
+      if (slot < cap) picked[slot] = (long long)(row_offset + (uint64_t)i);
+    }
+  }
+}
+
+int launch_sample(const void* d2, long long n, int dtype, double eop, uint64_t seed, uint64_t off,
+                  long long* picked, long long cap, int* n_picked, cudaStream_t s) {
+  if (n == 0) return 0;
+  long long nb = (n + 255) / 256; if (nb > 148 * 8) nb = 148 * 8;
+  if (dtype == BKM_F32)
+    sample_kernel<float><<<(int)nb, 256, 0, s>>>((const float*)d2, n, eop, seed, off, picked, cap, n_picked);
+  else
+    sample_kernel<double><<<(int)nb, 256, 0, s>>>((const double*)d2, n, eop, seed, off, picked, cap, n_picked);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// transform: out[i][j] = sqrt(max(||x_i||^2 - 2 x_i.c_j + ||c_j||^2, 0))   (pairwise.py:79-97)
+// computed in the dtype of X like the reference does.  Output-bandwidth bound: each CTA stages
+// 64 rows, every thread produces (row, 4 centres) micro-tiles, results go out through smem so
+// the global stores are coalesced along k.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+transform_kernel(const T* __restrict__ X, long long n, int d, long long ldx,
+                 const unsigned char* __restrict__ pack, PackLayout L, T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int TR = 64;
+  const int k = L.k, d4 = L.d4;
+  T* xs = reinterpret_cast<T*>(smem);                // [TR][d4+1]
+  T* xn = xs + TR * (d4 + 1);                        // [TR]
+  const T* C = reinterpret_cast<const T*>(pack + L.off_cT);
+  const T* cn = reinterpret_cast<const T*>(pack + L.off_cnT);
+  const int tid = threadIdx.x;
+  const long long ntiles = (n + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long r0 = tile * TR;
+    const int rows = (int)min((long long)TR, n - r0);
+    __syncthreads();
+    for (int e = tid; e < rows * d; e += 256) {
+      int r = e / d, c = e - r * d;
+      xs[r * (d4 + 1) + c] = X[(r0 + r) * ldx + c];
+    }
+    __syncthreads();
+    if (tid < rows) {
+      T s = T(0);
+      for (int i = 0; i < d; ++i) { T v = xs[tid * (d4 + 1) + i]; s = fma(v, v, s); }
+      xn[tid] = s;
+    }
+    __syncthreads();
+    // thread -> (centre j fastest, row) so that stores are coalesced along k
+    for (long long e = tid; e < (long long)rows * k; e += 256) {
+      int r = (int)(e / k), j = (int)(e - (long long)r * k);
+      const T* xr = xs + r * (d4 + 1);
+      const T* cr = C + (size_t)j * d4;
+      T acc = T(0);
+      for (int i = 0; i < d; ++i) acc = fma(xr[i], cr[i], acc);
+      T v = xn[r] + cn[j] - T(2) * acc;
+      v = v > T(0) ? v : T(0);
+      out[(r0 + r) * (long long)k + j] = sqrt(v);
+    }
+  }
+}
+
+int launch_transform(const void* X, long long n, int d, long long ldx, int dtype,
+                     const void* pack, int k, void* out, int sm_count, cudaStream_t s) {
+  if (n == 0) return 0;
+  PackLayout L = pack_layout(k, d, dtype);
+  long long ntiles = (n + 63) / 64;
+  long long grid = (long long)sm_count * 4; if (grid > ntiles) grid = ntiles;
+  size_t esz = dtype == BKM_F64 ? 8 : 4;
+  size_t smem = (size_t)64 * (L.d4 + 1) * esz + 64 * esz + 16;
+  if (dtype == BKM_F32) {
+    BKM_CUDA_TRY(cudaFuncSetAttribute(transform_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transform_kernel<float><<<(int)grid, 256, smem, s>>>((const float*)X, n, d, ldx, (const unsigned char*)pack, L, (float*)out);
+  } else {
+    BKM_CUDA_TRY(cudaFuncSetAttribute(transform_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transform_kernel<double><<<(int)grid, 256, smem, s>>>((const double*)X, n, d, ldx, (const unsigned char*)pack, L, (double*)out);
+  }
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// NaN / inf scan (k_means.py:179-180)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void check_finite_kernel(const T* __restrict__ X, long long n, int d, long long ldx, int* flag) {
+  bool bad = false;
+  if (ldx == d) {
+    const long long tot = n * d;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot;
+         i += (long long)gridDim.x * blockDim.x) {
+      T v = X[i];
+      bad |= !(fabs((double)v) <= 1.7976931348623157e308);
+    }
+  } else {
+    for (long long r = blockIdx.x; r < n; r += gridDim.x)
+      for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        T v = X[r * ldx + c];
+        bad |= !(fabs((double)v) <= 1.7976931348623157e308);
+      }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+int launch_check_finite(const void* X, long long n, int d, long long ldx, int dtype, int* flag,
+                        int sm_count, cudaStream_t s) {
+  if (n == 0) return 0;
+  int grid = sm_count * 8;
+  if (dtype == BKM_F32) check_finite_kernel<float><<<grid, 256, 0, s>>>((const float*)X, n, d, ldx, flag);
+  else check_finite_kernel<double><<<grid, 256, 0, s>>>((const double*)X, n, d, ldx, flag);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bkm

@@ -1,0 +1,109 @@
+// bkm_common.cuh — shared definitions for the B200 KMeans hot-path kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/bkm_b200.h"
+
+#define BKM_CUDA_TRY(expr)                                  \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) { (void)cudaGetLastError(); return (int)_e; } \
+  } while (0)
+
+namespace bkm {
+
+// Counts kernel launches enqueued by the library (bench.py reports it as gpu_launches).
+extern long long g_launches;
+inline void note_launch(int n = 1) { g_launches += n; }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------
+// Centre pack: one device buffer holding every layout of the (k,d) centres the kernels use.
+// Built by pack_centers_kernel from the float64 centres (reference keeps centres in f64:
+// dask_ml/cluster/k_means.py:551-552).
+// ---------------------------------------------------------------------------------------
+struct PackLayout {
+  int k, d, dtype;
+  int d4;      // d rounded up to a multiple of 4 (SIMT row pitch, zero padded)
+  int kp;      // k rounded up to a multiple of 16 (UMMA N granularity)
+  int dk;      // d rounded up to a multiple of 32 (one 128-byte swizzle atom of fp32 per K-block)
+  size_t esz;  // sizeof(T)
+  size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, total;
+};
+
+static inline PackLayout pack_layout(int k, int d, int dtype) {
+  PackLayout L;
+  L.k = k; L.d = d; L.dtype = dtype;
+  L.d4 = (d + 3) / 4 * 4;
+  L.kp = (k + 15) / 16 * 16;
+  L.dk = (d + 31) / 32 * 32;
+  L.esz = dtype == BKM_F64 ? 8 : 4;
+  size_t o = 256;  // header
+  L.off_cT = o;   o = align_up(o + (size_t)k * L.d4 * L.esz, 256);
+  L.off_cnT = o;  o = align_up(o + (size_t)k * L.esz, 256);
+  L.off_c64 = o;  o = align_up(o + (size_t)k * d * 8, 256);
+  L.off_cn64 = o; o = align_up(o + (size_t)k * 8, 256);
+  L.off_bhi = o;  o = align_up(o + (size_t)L.kp * L.dk * 4, 256);
+  L.off_blo = o;  o = align_up(o + (size_t)L.kp * L.dk * 4, 256);
+  L.off_cn32 = o; o = align_up(o + (size_t)L.kp * 4, 256);
+  L.total = o;
+  return L;
+}
+
+// Header at the start of the pack (device memory).
+struct PackHeader {
+  int k, d, dtype, pad;
+  double cn_max;   // max_j ||c_j||^2 (float64) — used by the near-tie margin bound
+};
+
+// ---------------------------------------------------------------------------------------
+// Workspace for one chunk call: per-CTA partials.  Sized for the largest grid we launch.
+// ---------------------------------------------------------------------------------------
+static const int kMaxGrid = 148 * 8;
+
+struct WsLayout {
+  size_t off_psum, off_pcnt, off_pin, off_flag, total;
+  size_t psum_esz;
+};
+static inline WsLayout ws_layout(int d, int k, int dtype) {
+  WsLayout W;
+  W.psum_esz = dtype == BKM_F64 ? 8 : 4;
+  size_t o = 0;
+  W.off_psum = o; o = align_up(o + (size_t)kMaxGrid * k * d * W.psum_esz, 256);
+  W.off_pcnt = o; o = align_up(o + (size_t)kMaxGrid * k * 4, 256);
+  W.off_pin = o;  o = align_up(o + (size_t)kMaxGrid * 8, 256);
+  W.off_flag = o; o = align_up(o + 256, 256);
+  W.total = o;
+  return W;
+}
+
+// Arguments shared by the fused chunk kernels (passed by value as one struct).
+struct ChunkArgs {
+  const void* X;
+  long long n;
+  int d;
+  long long ldx;
+  const unsigned char* pack;
+  PackLayout L;
+  int k;
+  int* labels;        // nullable
+  void* min_out;      // nullable; x-dtype
+  int squared;        // 1: min_out/dist_sum are d^2 ; 0: sqrt(d^2)
+  void* psum;         // [grid][k][d] partial sums (M-step only)
+  int* pcnt;          // [grid][k]
+  double* pin;        // [grid] partial sum of min distances
+  float tau;          // near-tie margin coefficient (0 disables the f64 re-check)
+};
+
+// implemented in bkm_simt.cu
+int launch_simt(const ChunkArgs& a, bool mstep, int dtype, int sm_count, int* grid_out, cudaStream_t s);
+// implemented in bkm_tc.cu
+bool tc_supported(int d, int k, int dtype);
+int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
+// implemented in bkm_aux.cu
+int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
+                           double* sums, long long* counts, double* dist_sum, cudaStream_t s);
+
+}  // namespace bkm

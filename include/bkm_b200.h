@@ -1,0 +1,142 @@
+/*
+ * bkm_b200.h — C ABI of the B200-native KMeans hot path (libbkm_b200.so).
+ *
+ * This is the drop-in boundary for the per-chunk operators that the reference
+ * (mrocklin/dask-ml) invokes from its task graph.  dask-ml has no FFI layer of its
+ * own; the callables replaced here are the ones its graph calls per row-chunk:
+ *
+ *   reference per-chunk callable                                  replaced by
+ *   ------------------------------------------------------------  -------------------------
+ *   sklearn.metrics.pairwise_distances_argmin_min(x, Y, ...)      bkm_lloyd_chunk (E-step half)
+ *     dask_ml/metrics/pairwise.py:35-38                           bkm_assign_chunk
+ *   _centers_dense(X, labels, n_clusters, distances)              bkm_lloyd_chunk (M-step half)
+ *     dask_ml/cluster/k_means.py:572-582 (via da.atop :531-544)
+ *   da.bincount(labels, minlength=k)  k_means.py:548              bkm_lloyd_chunk (counts)
+ *   sum(r.to_delayed()) / counts, squared_norm(C - C')            bkm_finalize
+ *     k_means.py:545-555
+ *   metrics.pairwise_distances(x, Y).min(1)**2, p > U, where      bkm_assign_chunk + bkm_sample_chunk
+ *     k_means.py:466-491, pairwise.py:55-66
+ *   metrics.euclidean_distances(X, Y)  pairwise.py:69-97          bkm_transform_chunk
+ *   da.isnull(X).any(), da.isinf(X).any()  k_means.py:179-180     bkm_check_finite
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless its name ends in _host.
+ *   - return 0 on success, negative BKM_E* for argument errors, positive values are
+ *     forwarded cudaError_t codes.  Nothing throws across the ABI.
+ *   - nothing allocates: the caller owns every buffer (sizes from the *_bytes helpers).
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*).
+ *   - X chunks are row-major (C order), `ldx` = row pitch in ELEMENTS (>= d).
+ *   - There is NO CPU fallback: on a box without a GPU the compute entry points return
+ *     a CUDA error (the library still loads, so symbol checks work without a driver).
+ */
+#ifndef BKM_B200_H
+#define BKM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BKM_VERSION 100
+
+/* element types of X */
+#define BKM_F32 0
+#define BKM_F64 1
+
+/* error codes (negative) */
+#define BKM_OK            0
+#define BKM_EINVAL       -1   /* bad argument (null pointer, n<0, d<=0, k<=0, ldx<d ...) */
+#define BKM_EDTYPE       -2   /* unsupported x_dtype */
+#define BKM_EUNSUPPORTED -3   /* shape not supported by any kernel on this device */
+#define BKM_EWORKSPACE   -4   /* workspace too small */
+#define BKM_EALIGN       -5   /* pointer alignment requirement violated */
+
+/* flags */
+#define BKM_FLAG_FORCE_SIMT   1   /* never use the tcgen05 path (exact-fp32 CUDA-core kernel) */
+#define BKM_FLAG_FORCE_TC     2   /* fail with BKM_EUNSUPPORTED instead of falling back to SIMT */
+#define BKM_FLAG_NO_RECHECK   4   /* skip the float64 re-check of near-tie rows */
+
+int bkm_version(void);
+const char* bkm_error_string(int code);
+
+/* Device facts needed by the host: SM count and compute capability. */
+int bkm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* Which kernel family a (d, k, dtype, flags) problem dispatches to:
+ * 0 = SIMT (CUDA cores, fp32/fp64 exact), 1 = tcgen05 3xTF32 tensor-core path. <0 = error. */
+int bkm_kernel_family(int d, int k, int x_dtype, int flags);
+
+/* ---- centre pack -------------------------------------------------------------------
+ * Kernels read the centres from an opaque "pack" built on the device from the float64
+ * centres (the reference keeps centres in float64 from iteration 2 on: k_means.py:551-552).
+ * The pack holds the layouts each kernel family wants (padded fp32/fp64 rows and ||c||^2 for
+ * the CUDA-core kernels; -2c split into tf32 hi/lo operand tiles for tcgen05) plus the
+ * float64 originals used by the near-tie re-check. */
+int bkm_centers_pack_bytes(int k, int d, int x_dtype, size_t* out);
+int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype,
+                     void* pack, size_t pack_bytes, void* stream);
+
+/* Scratch for per-CTA partial sums / counts / inertia of one chunk call. */
+int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out);
+
+/* ---- fused E+M step for one row chunk ----------------------------------------------
+ * replaces: pairwise_distances_argmin_min (pairwise.py:35-38) + _centers_dense
+ * (k_means.py:572-582) + da.bincount (k_means.py:548) for ONE chunk.
+ *   labels   [n]    int32  out : argmin_j ||x_i - c_j||^2, ties -> lowest j
+ *   min_d2   [n]    x-dtype out, nullable : min_j ||x_i - c_j||^2 (clamped >= 0)
+ *   sums     [k*d]  float64 ACCUMULATED (+=)  : sum of rows per label
+ *   counts   [k]    int64   ACCUMULATED (+=)  : rows per label
+ *   inertia  [1]    float64 ACCUMULATED (+=)  : sum_i min_d2_i
+ * Accumulation across chunk calls on the same stream is in call order (the reference
+ * folds chunk partials sequentially in chunk order, k_means.py:545-547). */
+int bkm_lloyd_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
+                    const void* pack, int k,
+                    int32_t* labels, void* min_d2,
+                    double* sums, int64_t* counts, double* inertia,
+                    void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* ---- E-step only (predict, final re-label, k-means|| cost) ---------------------------
+ * replaces: pairwise_distances_argmin_min(X, centers[, squared]) per chunk.
+ *   min_dist [n] x-dtype out, nullable: squared ? d^2 : sqrt(d^2)
+ *   dist_sum [1] float64 ACCUMULATED: sum_i min_dist_i  (inertia, k_means.py:566; or
+ *                 the k-means|| cost phi, k_means.py:466-469, with squared=1)
+ *   labels nullable. */
+int bkm_assign_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
+                     const void* pack, int k,
+                     int32_t* labels, void* min_dist, int squared, double* dist_sum,
+                     void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* ---- k-means|| Bernoulli sampling (k_means.py:472-491) -------------------------------
+ * picked_i = (ell_over_phi * min_d2_i) > U_i with U_i = Philox4x32-10(seed, row_offset+i).
+ * Appends the GLOBAL row index (row_offset+i) of every picked row to picked[] (unordered,
+ * capacity `cap`), and adds the number of picked rows to *n_picked (may exceed cap: the
+ * caller then retries with a bigger buffer). */
+int bkm_sample_chunk(const void* min_d2, int64_t n, int x_dtype,
+                     double ell_over_phi, uint64_t seed, uint64_t row_offset,
+                     int64_t* picked, int64_t cap, int* n_picked, void* stream);
+
+/* ---- transform: full (n,k) euclidean distance block (pairwise.py:69-97) ---------------
+ * out [n*k] x-dtype, row-major: sqrt(max(||x||^2 - 2 x.c + ||c||^2, 0)). */
+int bkm_transform_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
+                        const void* pack, int k, void* out, void* stream);
+
+/* ---- centre update + shift (k_means.py:548-555), run after the cross-GPU allreduce ----
+ *   C_new = sums / max(counts,1)[:,None]   (empty cluster -> zero vector, Q1)
+ *   *shift = sum((C_old - C_new)^2)        (float64)                                  */
+int bkm_finalize(const double* sums, const int64_t* counts, const double* centers_old,
+                 double* centers_new, double* shift, int k, int d, void* stream);
+
+/* ---- NaN/inf scan of a chunk (k_means.py:179-180): sets *flag (int32) nonzero -------- */
+int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
+                     int* flag, void* stream);
+
+/* Number of kernel launches this library has enqueued since load (for bench accounting). */
+int64_t bkm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BKM_B200_H */

@@ -1,0 +1,170 @@
+"""GPU parity tests of the C-ABI chunk operators against the CPU oracle (run with -m gpu)."""
+import numpy as np
+import pytest
+
+from _util import assert_labels_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from dask_ml_b200.engine import CudaBackend
+
+    return CudaBackend()
+
+
+def _blobs(n, d, k_true, seed, dtype, scale=10.0, std=1.0):
+    rng = np.random.RandomState(seed)
+    cent = rng.uniform(-scale, scale, size=(k_true, d))
+    lab = rng.randint(0, k_true, size=n)
+    X = cent[lab] + std * rng.standard_normal((n, d))
+    return X.astype(dtype)
+
+
+SHAPES = [
+    # n, d, k, dtype
+    (1000, 4, 10, "float32"),
+    (777, 2, 3, "float32"),
+    (5000, 13, 20, "float32"),
+    (3001, 41, 100, "float32"),
+    (4096, 64, 256, "float32"),
+    (9000, 64, 256, "float32"),
+    (2500, 16, 8, "float64"),
+    (1200, 41, 100, "float64"),
+    (300, 128, 300, "float32"),     # k*d too large for the smem-resident mode -> GLOBAL mode
+    (100, 7, 1, "float32"),
+    (5, 3, 2, "float32"),
+]
+
+
+@pytest.mark.parametrize("n,d,k,dtype", SHAPES)
+@pytest.mark.parametrize("flags", [1, 0])      # 1 = FORCE_SIMT, 0 = auto (tcgen05 where supported)
+def test_lloyd_chunk_matches_oracle(be, oracle, n, d, k, dtype, flags):
+    import torch
+
+    be.flags = flags
+    X = _blobs(n, d, max(2, k // 2), 0, dtype)
+    C = X[np.random.RandomState(1).choice(n, k, replace=n < k)].astype(np.float64)
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    x = be.to_device(X, tdt)
+    pack = be.pack_centers(torch.as_tensor(C).to(be.device), tdt)
+    labels = be.empty((n,), torch.int32)
+    mind2 = be.empty((n,), tdt)
+    sums = be.zeros((k * d,), torch.float64)
+    counts = be.zeros((k,), torch.int64)
+    inertia = be.zeros((1,), torch.float64)
+    be.lloyd_chunk(x, pack, k, labels, mind2, sums, counts, inertia)
+    torch.cuda.synchronize()
+
+    (olab,), (omin,) = oracle.pairwise_distances_argmin_min([X], C.astype(dtype) if dtype == "float64" else C,
+                                                          metric_kwargs={"squared": True})
+    got = labels.cpu().numpy()
+    assert_labels_match(got, olab, X, C)
+    # M-step against the oracle scatter-add evaluated on the GPU's own labels (exactly comparable)
+    osums = oracle.centers_dense(X, got, k)
+    np.testing.assert_allclose(sums.cpu().numpy().reshape(k, d), osums, rtol=2e-6, atol=1e-6 * np.abs(osums).max())
+    np.testing.assert_array_equal(counts.cpu().numpy(), np.bincount(got, minlength=k))
+    # min distance and inertia
+    gmin = mind2.cpu().numpy().astype(np.float64)
+    scale = (X.astype(np.float64) ** 2).sum(1) + (C ** 2).sum(1).max()
+    tol = 2e-6 if dtype == "float32" else 1e-12
+    assert np.max(np.abs(gmin - omin) / scale) < tol
+    assert abs(inertia.item() - omin.sum()) <= 1e-5 * max(1.0, omin.sum())
+    be.flags = 0
+
+
+def test_assign_non_contiguous_rows(be, oracle):
+    import torch
+
+    rng = np.random.RandomState(3)
+    big = rng.standard_normal((3000, 24)).astype(np.float32)
+    xb = torch.from_numpy(big).to(be.device)
+    x = xb[:, :13]                     # ldx = 24 > d = 13
+    C = big[:20, :13].astype(np.float64)
+    pack = be.pack_centers(torch.as_tensor(C).to(be.device), torch.float32)
+    labels = be.empty((3000,), torch.int32)
+    mn = be.empty((3000,), torch.float32)
+    acc = be.zeros((1,), torch.float64)
+    be.assign_chunk(x, pack, 20, labels, mn, False, acc)
+    (olab,), (omin,) = oracle.pairwise_distances_argmin_min([big[:, :13]], C)
+    assert_labels_match(labels.cpu().numpy(), olab, big[:, :13], C)
+    np.testing.assert_allclose(mn.cpu().numpy(), omin, rtol=1e-4, atol=1e-4)
+    assert abs(acc.item() - omin.sum()) < 1e-4 * omin.sum()
+
+
+def test_ties_go_to_lowest_index(be):
+    """Appendix B.1: duplicate centres -> the lower index wins."""
+    import torch
+
+    rng = np.random.RandomState(0)
+    X = rng.standard_normal((2000, 8)).astype(np.float32)
+    C = rng.standard_normal((6, 8))
+    C[4] = C[1]
+    C[5] = C[0]
+    pack = be.pack_centers(torch.as_tensor(C).to(be.device), torch.float32)
+    labels = be.empty((2000,), torch.int32)
+    acc = be.zeros((1,), torch.float64)
+    be.assign_chunk(be.to_device(X, torch.float32), pack, 6, labels, None, True, acc)
+    got = labels.cpu().numpy()
+    assert not np.isin(got, [4, 5]).any()
+
+
+def test_finalize_and_empty_cluster(be):
+    """Q1: empty cluster -> zero vector; shift = ||C - C'||_F^2."""
+    import torch
+
+    k, d = 5, 3
+    sums = torch.arange(k * d, dtype=torch.float64, device=be.device)
+    counts = torch.tensor([2, 0, 4, 1, 3], dtype=torch.int64, device=be.device)
+    sums.view(k, d)[1] = 0
+    Cold = torch.ones((k, d), dtype=torch.float64, device=be.device)
+    Cnew = be.empty((k, d), torch.float64)
+    shift = be.zeros((1,), torch.float64)
+    be.finalize(sums, counts, Cold, Cnew, shift)
+    want = sums.view(k, d).cpu().numpy() / np.maximum(counts.cpu().numpy(), 1)[:, None]
+    np.testing.assert_allclose(Cnew.cpu().numpy(), want, rtol=1e-15)
+    assert (Cnew.cpu().numpy()[1] == 0).all()
+    np.testing.assert_allclose(shift.item(), ((1 - want) ** 2).sum(), rtol=1e-14)
+
+
+def test_sample_matches_philox_restatement(be, oracle):
+    import torch
+
+    n = 20000
+    rng = np.random.RandomState(5)
+    d2 = rng.gamma(2.0, 1.0, size=n).astype(np.float32)
+    seed, off = 0x1234567890ABCDEF, 777
+    eop = 50.0 / d2.sum()
+    picked = be.empty((4096,), torch.int64)
+    cnt = be.zeros((1,), torch.int32)
+    be.sample_chunk(torch.from_numpy(d2).to(be.device), eop, seed, off, picked, cnt)
+    m = int(cnt.item())
+    got = np.sort(picked[:m].cpu().numpy())
+    u = oracle.philox_uniform(seed, np.arange(n, dtype=np.uint64) + np.uint64(off))
+    want = np.nonzero(eop * d2.astype(np.float64) > u)[0] + off
+    np.testing.assert_array_equal(got, want)
+
+
+def test_transform_chunk(be, oracle):
+    import torch
+
+    for dtype, tdt, tol in (("float32", torch.float32, 2e-3), ("float64", torch.float64, 1e-9)):
+        X = _blobs(1000, 13, 5, 0, dtype)
+        C = X[:7].astype(np.float64)
+        pack = be.pack_centers(torch.as_tensor(C).to(be.device), tdt)
+        out = be.empty((1000, 7), tdt)
+        be.transform_chunk(be.to_device(X, tdt), pack, 7, out)
+        want = oracle.euclidean_distances([X], C.astype(dtype))[0]
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-3, atol=tol)
+
+
+def test_check_finite(be):
+    import torch
+
+    X = np.random.RandomState(0).standard_normal((5000, 7)).astype(np.float32)
+    assert int(be.check_finite([be.to_device(X, torch.float32)]).item()) == 0
+    X[4321, 3] = np.inf
+    assert int(be.check_finite([be.to_device(X, torch.float32)]).item()) != 0
+    X[4321, 3] = np.nan
+    assert int(be.check_finite([be.to_device(X, torch.float64)]).item()) != 0

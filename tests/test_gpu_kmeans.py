@@ -1,0 +1,207 @@
+"""GPU end-to-end tests of the estimator against the CPU oracle and scikit-learn, modelled on the
+reference's tests/test_kmeans.py (run with -m gpu)."""
+import numpy as np
+import pytest
+import sklearn.datasets
+from sklearn.cluster import KMeans as SKKMeans, kmeans_plusplus
+
+from _util import assert_labels_match
+
+pytestmark = pytest.mark.gpu
+
+
+def _easy_blobs(oracle):
+    centers = np.array([[-7, -7], [0, 0], [7, 7]])
+    Xs, ys = oracle.make_blobs(cluster_std=0.1, centers=centers, chunks=50, random_state=0)
+    return Xs, ys
+
+
+def replace(a, old, new):
+    arr = np.empty(a.max() + 1, dtype=new.dtype)
+    arr[old] = new
+    return arr[a]
+
+
+def test_fit_given_init_matches_oracle_and_sklearn(oracle):
+    """tests/test_kmeans.py:87-98 — identical init => identical result."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    X_, _ = sklearn.datasets.make_blobs(n_samples=1000, n_features=4, random_state=1)
+    init, _ = kmeans_plusplus(X_, 3, random_state=np.random.RandomState(0))
+    X = ChunkedArray.from_array(X_, chunks=500)
+    dkkm = KMeans(3, init=init, random_state=0).fit(X)
+    skkm = SKKMeans(3, init=init, random_state=0, n_init=1).fit(X_)
+    lab, inertia, C, n_iter = oracle.kmeans_single_lloyd(oracle.to_blocks(X_, 500), 3, init=init)
+    np.testing.assert_allclose(dkkm.inertia_, skkm.inertia_)
+    np.testing.assert_allclose(dkkm.inertia_, inertia, rtol=1e-12)
+    assert dkkm.n_iter_ == n_iter
+    np.testing.assert_array_equal(dkkm.labels_.compute(), np.concatenate(lab))
+    np.testing.assert_allclose(dkkm.cluster_centers_, C, rtol=1e-12)
+
+
+def test_basic_vs_sklearn(oracle):
+    """tests/test_kmeans.py:55-85 (default init='k-means||')."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    Xs, _ = _easy_blobs(oracle)
+    X = ChunkedArray(Xs)
+    Xn = np.concatenate(Xs)
+    a = KMeans(n_clusters=3, random_state=0).fit(X)
+    b = SKKMeans(n_clusters=3, random_state=0, n_init=10).fit(Xn)
+    assert abs(a.inertia_ - b.inertia_) < 0.01
+    a_order = np.argsort(a.cluster_centers_, 0)[:, 0]
+    b_order = np.argsort(b.cluster_centers_, 0)[:, 0]
+    a_centers = a.cluster_centers_[a_order]
+    b_centers = b.cluster_centers_[b_order]
+    np.testing.assert_allclose(a_centers, b_centers, rtol=1e-3)
+    b_labels = replace(b.labels_, [0, 1, 2], a_order[b_order]).astype(b.labels_.dtype)
+    np.testing.assert_array_equal(a.labels_.compute(), b_labels)
+    assert a.n_iter_
+    b.cluster_centers_ = b_centers
+    a.cluster_centers_ = a_centers
+    np.testing.assert_allclose(a.transform(X).compute(), b.transform(Xn), rtol=1e-3)
+    np.testing.assert_array_equal(a.predict(X).compute(), b.predict(Xn))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("n,d,k,chunks", [(20000, 64, 256, 7000), (30000, 41, 100, 30000), (50000, 13, 20, 12500)])
+def test_lloyd_parity_fixed_init(oracle, dtype, n, d, k, chunks):
+    """North-star parity: identical inputs + identical init centroids -> labels equal (modulo float64
+    near-ties), inertia within 1e-4 relative (here far tighter), same n_iter, same centres."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    rng = np.random.RandomState(42)
+    cent = rng.uniform(-10, 10, size=(max(2, k // 3), d))
+    X = (cent[rng.randint(0, len(cent), size=n)] + rng.standard_normal((n, d))).astype(dtype)
+    init = X[:k].copy()
+    km = KMeans(k, init=init, max_iter=8, tol=1e-4).fit(ChunkedArray.from_array(X, chunks))
+    lab, inertia, C, n_iter = oracle.kmeans_single_lloyd(oracle.to_blocks(X, chunks), k, init=init, max_iter=8,
+                                                        tol=1e-4)
+    assert km.n_iter_ == n_iter
+    np.testing.assert_allclose(km.cluster_centers_, C, rtol=1e-4, atol=1e-5)
+    assert_labels_match(km.labels_.compute(), np.concatenate(lab), X, C, rtol=1e-6)
+    assert abs(km.inertia_ - inertia) <= 1e-6 * inertia
+    assert km.cluster_centers_.dtype == X.dtype
+    assert km.labels_.dtype == np.int32
+    assert isinstance(km.inertia_, np.float64)
+
+
+def test_converged_branch_and_old_centres(oracle):
+    """Q3/Q4: on convergence the OLD centres are returned and, when shift <= 1e-7, inertia is the sum
+    of SQUARED distances of the last E-step; otherwise the sum of plain distances after a re-label."""
+    from dask_ml_b200.cluster import KMeans
+
+    Xs, _ = _easy_blobs(oracle)
+    X = np.concatenate(Xs)
+    init = np.array([[-7.0, -7.0], [0.0, 0.0], [7.0, 7.0]])
+    for tol, max_iter in ((1e-4, 300), (0.5, 300), (0.0, 3)):
+        km = KMeans(3, init=init, tol=tol, max_iter=max_iter).fit(X)
+        lab, inertia, C, n_iter = oracle.kmeans_single_lloyd(oracle.to_blocks(X, 50), 3, init=init, tol=tol,
+                                                            max_iter=max_iter)
+        assert km.n_iter_ == n_iter
+        np.testing.assert_allclose(km.inertia_, inertia, rtol=1e-9)
+        np.testing.assert_allclose(km.cluster_centers_, C, rtol=1e-12, atol=1e-14)
+
+
+def test_empty_cluster_goes_to_origin(oracle):
+    """Q1: a centre that attracts no rows becomes the zero vector (no relocation)."""
+    from dask_ml_b200.cluster import KMeans
+
+    rng = np.random.RandomState(0)
+    X = rng.standard_normal((500, 3)) + 5.0
+    init = np.vstack([X[:2], [[100.0, 100.0, 100.0]]])
+    km = KMeans(3, init=init, max_iter=1, tol=0.0).fit(X)
+    lab, inertia, C, n_iter = oracle.kmeans_single_lloyd([X], 3, init=init, max_iter=1, tol=0.0)
+    np.testing.assert_allclose(km.cluster_centers_, C, rtol=1e-12, atol=1e-14)
+    assert (km.cluster_centers_[2] == 0).all()
+    np.testing.assert_allclose(km.inertia_, inertia, rtol=1e-9)
+
+
+def test_kmeanspp_and_random_init(oracle):
+    """tests/test_kmeans.py:100-117."""
+    from dask_ml_b200.cluster import KMeans
+
+    Xs, _ = _easy_blobs(oracle)
+    X = np.concatenate(Xs)
+    a = KMeans(3, init="k-means++", random_state=np.random.RandomState(0)).fit(X)
+    b = SKKMeans(3, init="k-means++", random_state=np.random.RandomState(0), n_init=1).fit(X)
+    assert abs(a.inertia_ - b.inertia_) < 1e-4 or abs(np.sqrt(a.inertia_) - np.sqrt(b.inertia_)) < 1.0
+    assert a.init == "k-means++"
+    KMeans(3, init="k-means++").fit(X)
+    KMeans(3, init="random", random_state=0).fit(X)
+
+
+def test_too_small_and_inputs():
+    """tests/test_kmeans.py:39-42,149-160: default k=8 on 20 rows; ndarray / chunked / DataFrame / tensor."""
+    import pandas as pd
+    import torch
+
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    rng = np.random.RandomState(0)
+    KMeans().fit(ChunkedArray.from_array(rng.uniform(size=(20, 2)), 10))
+    for X in (rng.uniform(size=(100, 4)),
+              ChunkedArray.from_array(rng.uniform(size=(100, 4)), (10, 4)),
+              pd.DataFrame(rng.uniform(size=(100, 4))),
+              torch.rand(100, 4, device="cuda"),
+              rng.randint(0, 50, size=(100, 4)).astype(np.int32),
+              rng.randint(0, 50, size=(100, 4)).astype(np.int64)):
+        km = KMeans(n_clusters=3).fit(X)
+        t = km.transform(X)
+        assert t.shape == (100, 3)
+
+
+def test_fit_raises():
+    """tests/test_kmeans.py:45-51 and NaN/inf handling (k_means.py:179-185)."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    km = KMeans()
+    with pytest.raises(ValueError):
+        km.fit(np.array([]).reshape(0, 1))
+    with pytest.raises(ValueError):
+        km.fit(np.array([]).reshape(1, 0))
+    X = np.random.RandomState(0).uniform(size=(100, 3))
+    X[7, 1] = np.nan
+    with pytest.raises(ValueError):
+        km.fit(ChunkedArray.from_array(X, 25))
+    X[7, 1] = np.inf
+    with pytest.raises(ValueError):
+        km.fit(ChunkedArray.from_array(X.astype(np.float32), 25))
+
+
+def test_dtypes():
+    """tests/test_kmeans.py:168-182."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    X = np.random.RandomState(0).uniform(size=(100, 2))
+    X2 = X.astype("f4")
+    for xx, yy in [(X, X), (X2, X2), (X, X2), (X2, X)]:
+        a = KMeans().fit(ChunkedArray.from_array(xx, 50))
+        b = SKKMeans(n_init=1).fit(xx)
+        assert a.cluster_centers_.dtype == b.cluster_centers_.dtype
+        assert a.inertia_.dtype == np.float64
+        assert a.labels_.dtype == b.labels_.dtype
+        assert a.transform(xx).dtype == b.transform(xx).dtype
+        assert a.transform(yy).dtype == b.transform(yy).dtype
+
+
+def test_kmeans_parallel_init_quality(oracle):
+    """k-means|| (init_scalable): with enough rounds the candidate set covers every blob, so the fit
+    reaches the same inertia as scikit-learn's (smoke-level pin)."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    rng = np.random.RandomState(1)
+    cent = rng.uniform(-20, 20, size=(5, 8))
+    X = (cent[rng.randint(0, 5, size=20000)] + 0.2 * rng.standard_normal((20000, 8))).astype(np.float32)
+    a = KMeans(5, random_state=0, oversampling_factor=10).fit(ChunkedArray.from_array(X, 6000))
+    b = SKKMeans(5, random_state=0, n_init=10).fit(X)
+    # inertia_ follows the reference's Q4 rule; compare through predict on the fitted centres
+    d = ((X[:, None, :].astype(np.float64) - a.cluster_centers_[None].astype(np.float64)) ** 2).sum(-1).min(1).sum()
+    assert d <= 1.05 * b.inertia_
