@@ -434,13 +434,17 @@ class LloydState(object):
         self.labels = [be.empty((int(x.shape[0]),), torch.int32) for x in X.chunks]
         self.pack = None
 
-    def step(self):
+    def step(self, kernel_events=None):
         be, X, k = self.be, self.X, self.k
         self.pack = be.pack_centers(self.C, X.dtype, out=self.pack)
         self.red.zero_()
         self.counts.zero_()
+        if kernel_events is not None:       # bench.py: CUDA events around the fused chunk kernel(s)
+            kernel_events[0].record()
         for x, lab in zip(X.chunks, self.labels):
             be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts, self.inertia)
+        if kernel_events is not None:
+            kernel_events[1].record()
         if X.comm.world > 1:
             self.counts_f.copy_(self.counts)
             X.comm.allreduce_sum_(self.red)
@@ -509,3 +513,78 @@ def _kmeans_single_lloyd(
     labels = ChunkedArray(st.labels)
     centers = st.C.cpu().numpy().astype(dt)
     return labels, np.float64(inertia), centers, i + 1
+
+
+def lloyd_iteration_host(X_host, centers, backend=None, comm=None, block_rows=1 << 20):
+    """One Lloyd iteration (k_means.py:523-555) over a HOST-resident row chunk.
+
+    ``X_host`` is a (n, d) float32/float64 torch CPU tensor (pinned memory makes the copies
+    asynchronous) or numpy array.  Row blocks are streamed host->device through two device buffers
+    on a copy stream while the fused E+M kernel consumes the previous block, so X crosses PCIe exactly
+    once per iteration; then the all-reduce, the centre update and a device->host read of the result.
+    Returns ``(new_centers float64 (k,d), inertia float64, shift float64)`` on the host.
+    This is the ingestion path for data that is not (or does not fit) resident in HBM.
+    """
+    be = backend or _get_backend()
+    comm = comm or Comm()
+    if not _is_torch(X_host):
+        X_host = torch.from_numpy(np.ascontiguousarray(X_host))
+    n, d = int(X_host.shape[0]), int(X_host.shape[1])
+    dt = X_host.dtype
+    centers = np.ascontiguousarray(centers, dtype=np.float64)
+    k = int(centers.shape[0])
+    cache = getattr(be, "_host_iter_cache", None)
+    key = (block_rows, d, dt, k)
+    if cache is None or cache["key"] != key:
+        cache = {
+            "key": key,
+            "bufs": [be.empty((block_rows, d), dt) for _ in range(2)],
+            "copy_stream": torch.cuda.Stream(device=be.device),
+            "red": be.zeros((k * d + k + 1,), torch.float64),
+            "counts": be.zeros((k,), torch.int64),
+            "C": be.empty((k, d), torch.float64),
+            "C_new": be.empty((k, d), torch.float64),
+            "shift": be.zeros((1,), torch.float64),
+            "pack": None,
+            "out_host": torch.empty((k * d + 2,), dtype=torch.float64).pin_memory(),
+        }
+        be._host_iter_cache = cache
+    bufs, cs = cache["bufs"], cache["copy_stream"]
+    red, counts = cache["red"], cache["counts"]
+    sums, counts_f, inertia = red[: k * d], red[k * d: k * d + k], red[k * d + k:]
+    main = torch.cuda.current_stream(be.device)
+    cache["C"].copy_(torch.from_numpy(centers), non_blocking=True)
+    cache["pack"] = be.pack_centers(cache["C"], dt, out=cache["pack"])
+    red.zero_()
+    counts.zero_()
+    copied = [None, None]
+    consumed = [None, None]
+    nblk = (n + block_rows - 1) // block_rows
+    for b in range(nblk):
+        s0 = b * block_rows
+        m = min(block_rows, n - s0)
+        slot = b & 1
+        with torch.cuda.stream(cs):
+            if consumed[slot] is not None:
+                cs.wait_event(consumed[slot])
+            bufs[slot][:m].copy_(X_host[s0:s0 + m], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            copied[slot] = ev
+        main.wait_event(copied[slot])
+        be.lloyd_chunk(bufs[slot][:m], cache["pack"], k, None, None, sums, counts, inertia)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        consumed[slot] = ev
+    if comm.world > 1:
+        counts_f.copy_(counts)
+        comm.allreduce_sum_(red)
+        counts.copy_(counts_f.round())
+    be.finalize(sums, counts, cache["C"], cache["C_new"], cache["shift"])
+    out = cache["out_host"]
+    out[: k * d].copy_(cache["C_new"].view(-1), non_blocking=True)
+    out[k * d: k * d + 1].copy_(inertia, non_blocking=True)
+    out[k * d + 1:].copy_(cache["shift"], non_blocking=True)
+    main.synchronize()
+    res = out.numpy()
+    return res[: k * d].reshape(k, d).copy(), float(res[k * d]), float(res[k * d + 1])

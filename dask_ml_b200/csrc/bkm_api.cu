@@ -68,8 +68,15 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (family < 0) return family;
   a.tau = tau_for(d, x_dtype, flags, family);
   int grid = 0;
-  if (family == 1) rc = launch_tc(a, mstep, sm, &grid, s);
-  else rc = launch_simt(a, mstep, x_dtype, sm, &grid, s);
+  rc = BKM_EALIGN;
+  if (family == 1) {
+    rc = launch_tc(a, mstep, sm, &grid, s);
+    if (rc == BKM_EALIGN && !(flags & BKM_FLAG_FORCE_TC)) {   // TMA needs 16-byte aligned rows
+      family = 0;
+      a.tau = tau_for(d, x_dtype, flags, 0);
+    }
+  }
+  if (family == 0) rc = launch_simt(a, mstep, x_dtype, sm, &grid, s);
   if (rc) return rc;
   return launch_reduce_partials(a, grid, mstep, x_dtype, sums, counts, dist_sum, s);
 }

@@ -164,7 +164,7 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
     const bool valid = tid < rows;
     T best = inf_of<T>(), second = inf_of<T>();
     int bj = 0;
-    T xn = T(0);
+    T xn = T(0), dexact = T(0);
     int my_slot = -1;
     if (valid) {
       const T* xr = xs + tid * pitch;
@@ -199,6 +199,20 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
         }
       }
       lab_s[tid] = bj;
+      {
+        // winning distance re-evaluated in direct form sum (x-c)^2: error relative to the distance
+        // itself, not to ||x||^2 (no cancellation) -> rows that coincide with a centre give 0.
+        const T* cw = (GLOBAL ? gC : cs) + (size_t)bj * d4;
+        T s = T(0);
+        for (int ch = 0; ch < nch; ++ch) {
+          T xv[4], cv[4];
+          ld4<T>(xr + ch * 4, xv);
+          ld4<T>(cw + ch * 4, cv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { T df = xv[q] - cv[q]; s = fma(df, df, s); }
+        }
+        dexact = s;
+      }
       if (a.tau > 0.f && k > 1) {
         T bound = (T)a.tau * (xn + cnmax);
         if (!(second - best > bound)) {          // also catches NaN
@@ -248,7 +262,7 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
       double d2;
       int lbl = lab_s[tid];
       if (my_slot >= 0) d2 = red2_s[my_slot];
-      else { T t = best + xn; d2 = (double)(t > T(0) ? t : T(0)); }
+      else d2 = (double)dexact;
       double outv = a.squared ? d2 : sqrt(d2);
       inertia_acc += outv;
       if (a.labels) a.labels[r0 + tid] = lbl;

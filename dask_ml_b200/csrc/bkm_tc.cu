@@ -1,6 +1,522 @@
-// placeholder — replaced by the tcgen05 kernel
+// bkm_tc.cu — fused E+M chunk kernel on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+// Shapes: fp32 X with d % 4 == 0, d <= 64, k <= 256 (BASELINE config C2: 10M x 64, k = 256).
+//
+// Per 128-row tile of X the kernel computes  S = X . (-2 C)^T  as a 3xTF32 split product
+//     S = Xhi.Bhi + Xhi.Blo + Xlo.Bhi          (B = -2C,  hi = tf32 part, lo = fp32 remainder)
+// which carries ~2^-21 relative error per product (fp32-GEMM class accuracy) instead of TF32's
+// 2^-11, so that labels agree with the reference's float64 E-step
+// (sklearn pairwise_distances_argmin_min, dask_ml/metrics/pairwise.py:35-38) except on near-ties.
+//   * X tiles arrive by TMA (SWIZZLE_128B, K-major) into a 3-stage shared-memory ring and are
+//     used as the A operand directly (the tensor core consumes the upper 19 bits = Xhi);
+//   * Xlo = X - Xhi is produced by the epilogue warps from the same smem tile and stored to
+//     TMEM (tcgen05.st); the third product takes A from TMEM;
+//   * B tiles (hi and lo, K-major SWIZZLE_128B) are loaded once per CTA and stay resident;
+//   * accumulators live in TMEM, two 128-column buffers ping-pong between the MMA issuer and the
+//     epilogue (a tile of k<=256 centres is processed as two "units" of <=128 columns);
+//   * epilogue: tcgen05.ld -> +||c||^2 -> running arg-min per row (lowest index wins ties),
+//     exact fp32 re-evaluation of the winning distance, label store;
+//   * M-step (_centers_dense, dask_ml/cluster/k_means.py:572-582): the smem-resident X tile is
+//     scatter-added into REGISTER-resident per-CTA sums: warp w owns clusters {w, w+8, ...},
+//     lane l owns features {l, l+32}; no atomics, no second read of X from HBM.
+//
+// Warp roles (512 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle
+//                           4-7 Xlo converter + epilogue (thread == row == TMEM lane)
+//                           8-15 M-step
 #include "bkm_common.cuh"
+#include <cuda.h>
+#include <math_constants.h>
+
 namespace bkm {
-bool tc_supported(int, int, int) { return false; }
-int launch_tc(const ChunkArgs&, bool, int, int*, cudaStream_t) { return BKM_EUNSUPPORTED; }
+
+static const int BM = 128;           // rows per tile
+static const int TC_THREADS = 512;
+static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
+
+struct TcCfg {
+  int KB;        // 32-float K-blocks per row (1 or 2)
+  int KS;        // MMA K-steps of 8 (ceil(d/8))
+  int NP;        // padded centre count (multiple of 16, <= 256)
+  int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
+  int U;
+  int NST;       // X stages
+  uint32_t off_bhi, off_blo, off_x, off_cn, off_lab, off_red, off_bar, off_tptr, total;
+};
+
+enum {
+  BAR_B_FULL = 0,
+  BAR_X_FULL = 1,       // [NST<=4]
+  BAR_X_EMPTY = 5,      // [4]
+  BAR_ACC_FULL = 9,     // [2]
+  BAR_ACC_EMPTY = 11,   // [2]
+  BAR_XLO_FULL = 13,    // [2]
+  BAR_LAB_FULL = 15,    // [2]
+  BAR_LAB_EMPTY = 17,   // [2]
+  BAR_COUNT = 19
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1u << 24)) __trap();     // a pipeline bug must fail, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+#define TC_LD16(taddr, r)                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                               \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                       \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),   \
+                 "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),            \
+                 "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                                 \
+               : "r"(taddr) : "memory")
+#define TC_ST32(taddr, r)                                                                              \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                         \
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                              \
+               "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                     \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),         \
+                 "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),       \
+                 "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),   \
+                 "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),   \
+                 "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+// 8-row x 128-byte swizzle atoms, SBO = 1024 B between atoms along M/N, LBO unused (1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (>>4), ignored for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset (>>4)
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// byte offset of 16-byte chunk q (0..7) of row r inside one swizzled K-block
+__device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4)); }
+
+#define ACC32_CASE(j) case j: acc[j][0] += x0; acc[j][1] += x1; break;
+
+template <bool MSTEP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
+                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  if (tid == 0 && (sbase & 1023)) __trap();
+  const uint32_t s_bhi = sbase + cfg.off_bhi, s_blo = sbase + cfg.off_blo, s_x = sbase + cfg.off_x;
+  float* cn_s = reinterpret_cast<float*>(smem + cfg.off_cn);
+  int* lab_s = reinterpret_cast<int*>(smem + cfg.off_lab);          // [2][BM]
+  double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [4]
+  const uint32_t bars = sbase + cfg.off_bar;
+  uint32_t* tptr_s = reinterpret_cast<uint32_t*>(smem + cfg.off_tptr);
+#define BAR(i) (bars + 8u * (uint32_t)(i))
+
+  const int NST = cfg.NST, KB = cfg.KB, KS = cfg.KS, NP = cfg.NP, U = cfg.U;
+  const uint32_t stage_bytes = (uint32_t)KB * KBLK_BYTES;
+  const long long ntiles = (a.n + BM - 1) / BM;
+  const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // ---------------- setup ----------------
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo));
+    mbar_init(BAR(BAR_B_FULL), 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(BAR(BAR_X_FULL + s), 1);
+      mbar_init(BAR(BAR_X_EMPTY + s), MSTEP ? 8 : 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR(BAR_ACC_FULL + b), 1);
+      mbar_init(BAR(BAR_ACC_EMPTY + b), 128);
+      mbar_init(BAR(BAR_XLO_FULL + b), 128);
+      mbar_init(BAR(BAR_LAB_FULL + b), 128);
+      mbar_init(BAR(BAR_LAB_EMPTY + b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tptr_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {
+    const float* gcn = reinterpret_cast<const float*>(a.pack + a.L.off_cn32);
+    for (int i = tid; i < NP; i += TC_THREADS) cn_s[i] = gcn[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr_s;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_expect_tx(BAR(BAR_B_FULL), 2u * (uint32_t)KB * (uint32_t)NP * 128u);
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_2d(s_bhi + (uint32_t)kb * NP * 128u, &tm_bhi, BAR(BAR_B_FULL), kb * 32, 0);
+        tma_load_2d(s_blo + (uint32_t)kb * NP * 128u, &tm_blo, BAR(BAR_B_FULL), kb * 32, 0);
+      }
+      for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const int stage = (int)(it % NST);
+        const uint32_t ph = (uint32_t)((it / NST) & 1);
+        mbar_wait(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
+        mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
+                      kb * 32, (int)(tile * BM));
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      mbar_wait(BAR(BAR_B_FULL), 0);
+      tc_fence_after();
+      for (long long it = 0; it < my_tiles; ++it) {
+        const int stage = (int)(it % NST);
+        const uint32_t ph = (uint32_t)((it / NST) & 1);
+        const uint32_t xs = s_x + stage * stage_bytes;
+        const uint32_t xlo_t = tmem + 256u + (uint32_t)(it & 1) * 64u;
+        mbar_wait(BAR(BAR_X_FULL + stage), ph);
+        tc_fence_after();
+        for (int u = 0; u < U; ++u) {
+          const long long g = it * U + u;
+          const int buf = (int)(g & 1);
+          mbar_wait(BAR(BAR_ACC_EMPTY + buf), (uint32_t)(((g >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
+          const uint32_t rowoff = u == 0 ? 0u : (uint32_t)cfg.NU0 * 128u;
+          const uint32_t idesc = make_idesc(ncols);
+          const uint32_t d_t = tmem + (uint32_t)buf * 128u;
+          // pass 1: Xhi . Bhi   (A = raw fp32 tile; the tensor core reads the tf32 part)
+          for (int s = 0; s < KS; ++s) {
+            const uint32_t ko = (uint32_t)(s >> 2) , ks = (uint32_t)(s & 3) * 32u;
+            mma_tf32_ss(d_t, make_desc(xs + ko * KBLK_BYTES + ks),
+                        make_desc(s_bhi + ko * NP * 128u + rowoff + ks), idesc, s > 0 ? 1u : 0u);
+          }
+          // pass 2: Xhi . Blo
+          for (int s = 0; s < KS; ++s) {
+            const uint32_t ko = (uint32_t)(s >> 2), ks = (uint32_t)(s & 3) * 32u;
+            mma_tf32_ss(d_t, make_desc(xs + ko * KBLK_BYTES + ks),
+                        make_desc(s_blo + ko * NP * 128u + rowoff + ks), idesc, 1u);
+          }
+          if (u == 0) {
+            mbar_wait(BAR(BAR_XLO_FULL + (it & 1)), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+          }
+          // pass 3: Xlo . Bhi   (A from TMEM)
+          for (int s = 0; s < KS; ++s) {
+            const uint32_t ko = (uint32_t)(s >> 2), ks = (uint32_t)(s & 3) * 32u;
+            mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, make_desc(s_bhi + ko * NP * 128u + rowoff + ks), idesc, 1u);
+          }
+          tc_commit(BAR(BAR_ACC_FULL + buf));
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================== Xlo converter + epilogue ===========================
+    const int q4 = warp - 4;
+    const int r = q4 * 32 + lane;                 // row in tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    double inertia_acc = 0.0;
+
+    auto convert = [&](long long it) {
+      const int stage = (int)(it % NST);
+      const uint32_t ph = (uint32_t)((it / NST) & 1);
+      mbar_wait(BAR(BAR_X_FULL + stage), ph);
+      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+      for (int kb = 0; kb < KB; ++kb) {
+        uint32_t v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + sw_chunk(r, q));
+          const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float hi = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);
+            const float lo = e[i] - hi;            // exact: the 13 low mantissa bits
+            uint32_t lo_t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_t) : "f"(lo));
+            v[q * 4 + i] = lo_t;
+          }
+        }
+        const uint32_t taddr = tmem + lane_addr + 256u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u;
+        TC_ST32(taddr, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
+    };
+
+    mbar_wait(BAR(BAR_B_FULL), 0);              // B tiles are read below through the generic proxy
+    if (my_tiles > 0) convert(0);
+    for (long long it = 0; it < my_tiles; ++it) {
+      if (it + 1 < my_tiles) convert(it + 1);
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const int stage = (int)(it % NST);
+      float best = CUDART_INF_F;
+      int bj = 0;
+      for (int u = 0; u < U; ++u) {
+        const long long g = it * U + u;
+        const int buf = (int)(g & 1);
+        const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
+        const int col0 = u == 0 ? 0 : cfg.NU0;
+        mbar_wait(BAR(BAR_ACC_FULL + buf), (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        for (int c = 0; c < ncols; c += 16) {
+          uint32_t v[16];
+          TC_LD16(tmem + lane_addr + (uint32_t)buf * 128u + (uint32_t)c, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + col0 + c + j4 * 4);
+            const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float dist = __uint_as_float(v[j4 * 4 + j]) + cn[j];
+              if (dist < best) { best = dist; bj = col0 + c + j4 * 4 + j; }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(BAR_ACC_EMPTY + buf));
+      }
+      // exact fp32 distance to the winner: sum (x - c)^2 with c = -(bhi + blo)/2
+      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+      float d2 = 0.f;
+      for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + sw_chunk(r, q));
+          const uint32_t bo = (uint32_t)kb * NP * 128u + sw_chunk(bj, q);
+          const float4 h4 = *reinterpret_cast<const float4*>(smem + cfg.off_bhi + bo);
+          const float4 l4 = *reinterpret_cast<const float4*>(smem + cfg.off_blo + bo);
+          float t;
+          t = fmaf(0.5f, h4.x + l4.x, x4.x); d2 = fmaf(t, t, d2);
+          t = fmaf(0.5f, h4.y + l4.y, x4.y); d2 = fmaf(t, t, d2);
+          t = fmaf(0.5f, h4.z + l4.z, x4.z); d2 = fmaf(t, t, d2);
+          t = fmaf(0.5f, h4.w + l4.w, x4.w); d2 = fmaf(t, t, d2);
+        }
+      }
+      const long long row = tile * BM + r;
+      const bool valid = row < a.n;
+      if (valid) {
+        const float outv = a.squared ? d2 : sqrtf(d2);
+        inertia_acc += (double)outv;
+        if (a.labels) a.labels[row] = bj;
+        if (a.min_out) reinterpret_cast<float*>(a.min_out)[row] = outv;
+      }
+      if (MSTEP) {
+        const int lb = (int)(it & 1);
+        mbar_wait(BAR(BAR_LAB_EMPTY + lb), (uint32_t)(((it >> 1) & 1) ^ 1));
+        lab_s[lb * BM + r] = valid ? bj : -1;
+        mbar_arrive(BAR(BAR_LAB_FULL + lb));       // release semantics order the smem store
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(BAR_X_EMPTY + stage));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, o);
+    if (lane == 0) red_s[q4] = inertia_acc;
+  } else if (warp >= 8) {
+    // =========================== M-step ===========================
+    if (MSTEP) {
+      const int wm = warp - 8;
+      float acc[32][2];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+      int cnt = 0;
+      const bool two = KB > 1;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const int stage = (int)(it % NST);
+        const int lb = (int)(it & 1);
+        mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+        mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+        const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+        for (int base = 0; base < BM; base += 32) {
+          const int ml = lab_s[lb * BM + base + lane];
+          unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int c = __shfl_sync(0xffffffffu, ml, b);
+            const int cl = c >> 3;
+            const int row = base + b;
+            const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
+            const float x0 = *reinterpret_cast<const float*>(xs + ro);
+            const float x1 = two ? *reinterpret_cast<const float*>(xs + KBLK_BYTES + ro) : 0.f;
+            switch (cl) {
+              ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)
+              ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)
+              ACC32_CASE(12) ACC32_CASE(13) ACC32_CASE(14) ACC32_CASE(15) ACC32_CASE(16) ACC32_CASE(17)
+              ACC32_CASE(18) ACC32_CASE(19) ACC32_CASE(20) ACC32_CASE(21) ACC32_CASE(22) ACC32_CASE(23)
+              ACC32_CASE(24) ACC32_CASE(25) ACC32_CASE(26) ACC32_CASE(27) ACC32_CASE(28) ACC32_CASE(29)
+              ACC32_CASE(30) ACC32_CASE(31)
+              default: break;
+            }
+            cnt += (lane == cl) ? 1 : 0;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+          mbar_arrive(BAR(BAR_X_EMPTY + stage));
+        }
+      }
+      // flush the register-resident sums: cluster c = wm + 8 j, features lane and lane + 32
+      float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = wm + 8 * j;
+        if (c < a.k) {
+          if (lane < a.d) g[(size_t)c * a.d + lane] = acc[j][0];
+          if (lane + 32 < a.d) g[(size_t)c * a.d + lane + 32] = acc[j][1];
+        }
+      }
+      const int cc = wm + 8 * lane;
+      if (cc < a.k) a.pcnt[(size_t)blockIdx.x * a.k + cc] = cnt;
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) a.pin[blockIdx.x] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+#undef BAR
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][cols] with row pitch `pitch_elems`, box = 32 columns x box_rows, 128B swizzle
+static int make_map(CUtensorMap* tm, const void* base, long long rows, int cols, long long pitch_elems, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return BKM_EUNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : BKM_EUNSUPPORTED;
+}
+
+bool tc_supported(int d, int k, int dtype) {
+  return dtype == BKM_F32 && d >= 4 && d <= 64 && (d % 4) == 0 && k >= 1 && k <= 256;
+}
+
+static bool make_cfg(int d, int k, TcCfg* c) {
+  c->KB = (d + 31) / 32;
+  c->KS = (d + 7) / 8;
+  c->NP = (k + 15) / 16 * 16;
+  if (c->NP <= 128) { c->NU0 = c->NP; c->NU1 = 0; c->U = 1; }
+  else { c->NU0 = (c->NP / 2 + 15) / 16 * 16; c->NU1 = c->NP - c->NU0; c->U = c->NU1 > 0 ? 2 : 1; }
+  const uint32_t bbytes = (uint32_t)c->KB * c->NP * 128u;
+  for (int nst = 3; nst >= 2; --nst) {
+    uint32_t o = 0;
+    c->off_bhi = o; o += bbytes;
+    c->off_blo = o; o += bbytes;
+    o = (uint32_t)align_up(o, 1024);
+    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;
+    c->off_cn = o; o += (uint32_t)c->NP * 4;
+    c->off_lab = o; o += 2 * BM * 4;
+    c->off_red = o; o += 32;
+    c->off_bar = o; o += BAR_COUNT * 8;
+    c->off_tptr = o; o += 16;
+    c->total = o;
+    c->NST = nst;
+    if (o <= 227 * 1024) return true;
+  }
+  return false;
+}
+
+int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
+  TcCfg cfg;
+  if (!make_cfg(a.d, a.k, &cfg)) return BKM_EUNSUPPORTED;
+  CUtensorMap tm_x, tm_bhi, tm_blo;
+  int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
+  if (rc) return rc;
+  rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
+  if (rc) return rc;
+  rc = make_map(&tm_blo, a.pack + a.L.off_blo, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
+  if (rc) return rc;
+  long long ntiles = (a.n + BM - 1) / BM;
+  int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
+  if (grid < 1) grid = 1;
+  *grid_out = grid;
+  if (mstep) {
+    BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.total));
+    tc_chunk_kernel<true><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);
+  } else {
+    BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.total));
+    tc_chunk_kernel<false><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);
+  }
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bkm

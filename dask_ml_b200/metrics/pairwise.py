@@ -66,6 +66,15 @@ def euclidean_distances(X, Y=None, Y_norm_squared=None, squared=False, X_norm_sq
     """
     if Y is None:
         raise NotImplementedError("Y=None (X against itself) is not on the KMeans path")
+    from ..cluster.k_means import _to_device_data
+
+    X = _to_device_data(X, check_finite=False)
+    Y = np.asarray(Y)
+    if X.dtype == torch.float32 and Y.dtype == np.float64:
+        # result dtype follows numpy promotion of (X, Y) like -2*dot(X, Y.T)+XX+YY in the reference
+        from ..engine import DeviceData
+
+        X = DeviceData([c.to(torch.float64) for c in X.chunks], X.backend, X.comm)
     X, be, pack, k = _prep(X, Y)
     if X_norm_squared is not None:
         XX = np.asarray(X_norm_squared)
