@@ -442,7 +442,8 @@ class LloydState(object):
         if kernel_events is not None:       # bench.py: CUDA events around the fused chunk kernel(s)
             kernel_events[0].record()
         for x, lab in zip(X.chunks, self.labels):
-            be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts, self.inertia)
+            # per-row distances are not needed inside the loop: the inertia is produced by relabel()
+            be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts, None)
         if kernel_events is not None:
             kernel_events[1].record()
         if X.comm.world > 1:
@@ -492,14 +493,17 @@ def _kmeans_single_lloyd(
     st = LloydState(X, np.asarray(centers))
     shift = None
     i = -1
+    accepted = False
     for i in range(max_iter):
         with _timer("Lloyd loop %2d." % i, _logger=logger):
             st.step()
             shift = float(st.shift.item())       # the one host sync per iteration (k_means.py:552)
             logger.info("Shift: %0.4f", shift)
+            accepted = False
             if shift < tol:
                 break                            # Q3: break BEFORE centers = new_centers
             st.accept()
+            accepted = True
 
     if shift is None:
         raise ValueError("max_iter must be at least 1, got %r" % (max_iter,))
@@ -508,7 +512,14 @@ def _kmeans_single_lloyd(
         # Q4: re-label against the current centres with the default (non-squared) metric
         inertia = float(st.relabel(squared=False).item())
     else:
-        inertia = float(st.inertia.item())
+        # Q4, other side: inertia = sum of the SQUARED distances of the last E-step, i.e. against the
+        # centres that E-step used.  The loop does not keep per-row distances, so they are produced here
+        # by one E-step-only pass against those same centres (labels are identical).
+        if accepted:
+            st.accept()                          # back to the centres of the last E-step
+        inertia = float(st.relabel(squared=True).item())
+        if accepted:
+            st.accept()
 
     labels = ChunkedArray(st.labels)
     centers = st.C.cpu().numpy().astype(dt)

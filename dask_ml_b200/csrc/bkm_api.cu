@@ -34,8 +34,11 @@ static int sm_count_of_current(int* out) {
 // sum|x_i c_i| <= (||x||^2+||c||^2)/2; both distances and the -2 factor give the constant.
 static float tau_for(int d, int dtype, int flags, int family) {
   if (dtype != BKM_F32 || (flags & BKM_FLAG_NO_RECHECK)) return 0.f;
-  float eps = family == 1 ? 1.0f / 1048576.0f   /* 3xTF32: ~2^-20 */
-                          : 1.0f / 16777216.0f; /* fp32 FMA chain: 2^-24 */
+  const float eps = 1.0f / 16777216.0f;   // 2^-24
+  // tcgen05 path: 3*ceil(d/8) accumulations into an fp32 TMEM accumulator of magnitude ~(||x||^2+||c||^2)
+  // plus the dropped lo*lo term of the 3xTF32 split (2^-21); measured worst margin of a flipped label on
+  // blobs data: 3.6e-7 -> the bound below (3.3e-6 at d=64) leaves ~9x headroom.
+  if (family == 1) return (8.0f * sqrtf(3.0f * (float)((d + 7) / 8)) + 16.0f) * eps;
   return 8.0f * (sqrtf((float)d) + 2.0f) * eps;
 }
 
@@ -49,8 +52,9 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (mstep && (!sums || !counts)) return BKM_EINVAL;
   if (n == 0) return 0;
   if (!X) return BKM_EINVAL;
-  WsLayout W = ws_layout(d, k, x_dtype);
+  WsLayout W = ws_layout(n, d, k, x_dtype);
   if (ws_bytes < W.total) return BKM_EWORKSPACE;
+  if (n > 0x7fffffffLL) return BKM_EUNSUPPORTED;      // row indices inside a chunk are 32-bit
   int sm = 0;
   int rc = sm_count_of_current(&sm);
   if (rc) return rc;
@@ -63,6 +67,10 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   a.psum = (unsigned char*)ws + W.off_psum;
   a.pcnt = (int*)((unsigned char*)ws + W.off_pcnt);
   a.pin = (double*)((unsigned char*)ws + W.off_pin);
+  a.want_sum = dist_sum != nullptr;
+  a.defer_cnt = (int*)((unsigned char*)ws + W.off_flag);
+  a.defer_idx = (int*)((unsigned char*)ws + W.off_defer);
+  a.out_sums = sums; a.out_counts = counts; a.out_dist_sum = dist_sum;
 
   int family = bkm_kernel_family(d, k, x_dtype, flags);
   if (family < 0) return family;
@@ -140,10 +148,9 @@ int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype, void* p
 }
 
 int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out) {
-  (void)n;
-  if (k <= 0 || d <= 0 || !out) return BKM_EINVAL;
+  if (k <= 0 || d <= 0 || n < 0 || !out) return BKM_EINVAL;
   if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
-  *out = ws_layout(d, k, x_dtype).total;
+  *out = ws_layout(n, d, k, x_dtype).total;
   return 0;
 }
 

@@ -64,17 +64,18 @@ struct PackHeader {
 static const int kMaxGrid = 148 * 8;
 
 struct WsLayout {
-  size_t off_psum, off_pcnt, off_pin, off_flag, total;
+  size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, total;
   size_t psum_esz;
 };
-static inline WsLayout ws_layout(int d, int k, int dtype) {
+static inline WsLayout ws_layout(long long n, int d, int k, int dtype) {
   WsLayout W;
   W.psum_esz = dtype == BKM_F64 ? 8 : 4;
   size_t o = 0;
   W.off_psum = o; o = align_up(o + (size_t)kMaxGrid * k * d * W.psum_esz, 256);
   W.off_pcnt = o; o = align_up(o + (size_t)kMaxGrid * k * 4, 256);
   W.off_pin = o;  o = align_up(o + (size_t)kMaxGrid * 8, 256);
-  W.off_flag = o; o = align_up(o + 256, 256);
+  W.off_flag = o; o = align_up(o + 256, 256);          // [0] = deferred-row counter
+  W.off_defer = o; o = align_up(o + (size_t)(n > 0 ? n : 0) * 4, 256);
   W.total = o;
   return W;
 }
@@ -95,6 +96,12 @@ struct ChunkArgs {
   int* pcnt;          // [grid][k]
   double* pin;        // [grid] partial sum of min distances
   float tau;          // near-tie margin coefficient (0 disables the f64 re-check)
+  int want_sum;       // caller wants the summed min distance (inertia / cost)
+  int* defer_cnt;     // tcgen05 path: number of rows deferred to the float64 re-check kernel
+  int* defer_idx;     // [n] their row indices
+  double* out_sums;   // final accumulators (the re-check kernel adds the deferred rows' contributions)
+  long long* out_counts;
+  double* out_dist_sum;
 };
 
 // implemented in bkm_simt.cu

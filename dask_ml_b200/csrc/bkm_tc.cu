@@ -40,7 +40,7 @@ struct TcCfg {
   int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
   int U;
   int NST;       // X stages
-  uint32_t off_bhi, off_blo, off_x, off_cn, off_lab, off_red, off_bar, off_tptr, total;
+  uint32_t off_bhi, off_blo, off_x, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
 };
 
 enum {
@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r
 
 #define ACC32_CASE(j) case j: acc[j][0] += x0; acc[j][1] += x1; break;
 
-template <bool MSTEP>
+template <bool MSTEP, bool WANT_DIST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
@@ -148,7 +148,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   const uint32_t s_bhi = sbase + cfg.off_bhi, s_blo = sbase + cfg.off_blo, s_x = sbase + cfg.off_x;
   float* cn_s = reinterpret_cast<float*>(smem + cfg.off_cn);
   int* lab_s = reinterpret_cast<int*>(smem + cfg.off_lab);          // [2][BM]
-  double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [4]
+  double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [5]
   const uint32_t bars = sbase + cfg.off_bar;
   uint32_t* tptr_s = reinterpret_cast<uint32_t*>(smem + cfg.off_tptr);
 #define BAR(i) (bars + 8u * (uint32_t)(i))
@@ -166,7 +166,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     mbar_init(BAR(BAR_B_FULL), 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(BAR(BAR_X_FULL + s), 1);
-      mbar_init(BAR(BAR_X_EMPTY + s), MSTEP ? 8 : 4);
+      mbar_init(BAR(BAR_X_EMPTY + s), 8);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
@@ -175,6 +175,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       mbar_init(BAR(BAR_LAB_FULL + b), 128);
       mbar_init(BAR(BAR_LAB_EMPTY + b), 8);
     }
+    red_s[8] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -198,6 +199,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         tma_load_2d(s_bhi + (uint32_t)kb * NP * 128u, &tm_bhi, BAR(BAR_B_FULL), kb * 32, 0);
         tma_load_2d(s_blo + (uint32_t)kb * NP * 128u, &tm_blo, BAR(BAR_B_FULL), kb * 32, 0);
       }
+#pragma unroll 1
       for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * gridDim.x;
         const int stage = (int)(it % NST);
@@ -214,6 +216,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     if (lane == 0) {
       mbar_wait(BAR(BAR_B_FULL), 0);
       tc_fence_after();
+#pragma unroll 1
       for (long long it = 0; it < my_tiles; ++it) {
         const int stage = (int)(it % NST);
         const uint32_t ph = (uint32_t)((it / NST) & 1);
@@ -221,6 +224,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         const uint32_t xlo_t = tmem + 256u + (uint32_t)(it & 1) * 64u;
         mbar_wait(BAR(BAR_X_FULL + stage), ph);
         tc_fence_after();
+#pragma unroll 1
         for (int u = 0; u < U; ++u) {
           const long long g = it * U + u;
           const int buf = (int)(g & 1);
@@ -231,12 +235,14 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
           const uint32_t idesc = make_idesc(ncols);
           const uint32_t d_t = tmem + (uint32_t)buf * 128u;
           // pass 1: Xhi . Bhi   (A = raw fp32 tile; the tensor core reads the tf32 part)
+#pragma unroll 1
           for (int s = 0; s < KS; ++s) {
             const uint32_t ko = (uint32_t)(s >> 2) , ks = (uint32_t)(s & 3) * 32u;
             mma_tf32_ss(d_t, make_desc(xs + ko * KBLK_BYTES + ks),
                         make_desc(s_bhi + ko * NP * 128u + rowoff + ks), idesc, s > 0 ? 1u : 0u);
           }
           // pass 2: Xhi . Blo
+#pragma unroll 1
           for (int s = 0; s < KS; ++s) {
             const uint32_t ko = (uint32_t)(s >> 2), ks = (uint32_t)(s & 3) * 32u;
             mma_tf32_ss(d_t, make_desc(xs + ko * KBLK_BYTES + ks),
@@ -247,6 +253,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
             tc_fence_after();
           }
           // pass 3: Xlo . Bhi   (A from TMEM)
+#pragma unroll 1
           for (int s = 0; s < KS; ++s) {
             const uint32_t ko = (uint32_t)(s >> 2), ks = (uint32_t)(s & 3) * 32u;
             mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, make_desc(s_bhi + ko * NP * 128u + rowoff + ks), idesc, 1u);
@@ -260,13 +267,13 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     const int q4 = warp - 4;
     const int r = q4 * 32 + lane;                 // row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    double inertia_acc = 0.0;
-
+    float xn_next = 0.f;
     auto convert = [&](long long it) {
       const int stage = (int)(it % NST);
       const uint32_t ph = (uint32_t)((it / NST) & 1);
       mbar_wait(BAR(BAR_X_FULL + stage), ph);
       const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+      float xn4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int kb = 0; kb < KB; ++kb) {
         uint32_t v[32];
 #pragma unroll
@@ -275,6 +282,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
           const float e[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
+            xn4[i] = fmaf(e[i], e[i], xn4[i]);
             const float hi = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);
             const float lo = e[i] - hi;            // exact: the 13 low mantissa bits
             uint32_t lo_t;
@@ -285,109 +293,146 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         const uint32_t taddr = tmem + lane_addr + 256u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u;
         TC_ST32(taddr, v);
       }
+      xn_next = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
     };
 
     mbar_wait(BAR(BAR_B_FULL), 0);              // B tiles are read below through the generic proxy
+    const float cnmax = (float)reinterpret_cast<const PackHeader*>(a.pack)->cn_max;
     if (my_tiles > 0) convert(0);
+#pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
+      const float xn = xn_next;
       if (it + 1 < my_tiles) convert(it + 1);
       const long long tile = blockIdx.x + it * gridDim.x;
       const int stage = (int)(it % NST);
-      float best = CUDART_INF_F;
-      int bj = 0;
+      // four independent (best, second, argmin) trackers over column classes j % 4 break the
+      // serial min chain; they are merged after the last unit (lowest index wins ties).
+      float tb[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+      float ts[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+      int tj[4] = {0, 0, 0, 0};
+#define EPI_PROCESS(V, COLBASE)                                                          \
+  {                                                                                      \
+    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
+      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
+      const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};                                  \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                    \
+        const float dist = __uint_as_float(V[j4 * 4 + j]) + cn[j];                       \
+        ts[j] = fminf(ts[j], fmaxf(tb[j], dist));                                        \
+        if (dist < tb[j]) { tb[j] = dist; tj[j] = (COLBASE) + j4 * 4 + j; }              \
+      }                                                                                  \
+    }                                                                                    \
+  }
+#pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const long long g = it * U + u;
         const int buf = (int)(g & 1);
-        const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
+        const int nch = (u == 0 ? cfg.NU0 : cfg.NU1) >> 4;
         const int col0 = u == 0 ? 0 : cfg.NU0;
         mbar_wait(BAR(BAR_ACC_FULL + buf), (uint32_t)((g >> 1) & 1));
         tc_fence_after();
-        for (int c = 0; c < ncols; c += 16) {
-          uint32_t v[16];
-          TC_LD16(tmem + lane_addr + (uint32_t)buf * 128u + (uint32_t)c, v);
+        const uint32_t tbase = tmem + lane_addr + (uint32_t)buf * 128u;
+        uint32_t v0[16], v1[16];
+        TC_LD16(tbase, v0);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + col0 + c + j4 * 4);
-            const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float dist = __uint_as_float(v[j4 * 4 + j]) + cn[j];
-              if (dist < best) { best = dist; bj = col0 + c + j4 * 4 + j; }
-            }
+          if (c + 1 < nch) TC_LD16(tbase + (uint32_t)(c + 1) * 16u, v1);
+          EPI_PROCESS(v0, col0 + c * 16)
+          if (c + 1 < nch) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c + 2 < nch) TC_LD16(tbase + (uint32_t)(c + 2) * 16u, v0);
+            EPI_PROCESS(v1, col0 + (c + 1) * 16)
           }
         }
         tc_fence_before();
         mbar_arrive(BAR(BAR_ACC_EMPTY + buf));
       }
-      // exact fp32 distance to the winner: sum (x - c)^2 with c = -(bhi + blo)/2
-      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
-      float d2 = 0.f;
-      for (int kb = 0; kb < KB; ++kb) {
+#undef EPI_PROCESS
+      float best = CUDART_INF_F, second = CUDART_INF_F;
+      int bj = 0x7fffffff;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 x4 = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + sw_chunk(r, q));
-          const uint32_t bo = (uint32_t)kb * NP * 128u + sw_chunk(bj, q);
-          const float4 h4 = *reinterpret_cast<const float4*>(smem + cfg.off_bhi + bo);
-          const float4 l4 = *reinterpret_cast<const float4*>(smem + cfg.off_blo + bo);
-          float t;
-          t = fmaf(0.5f, h4.x + l4.x, x4.x); d2 = fmaf(t, t, d2);
-          t = fmaf(0.5f, h4.y + l4.y, x4.y); d2 = fmaf(t, t, d2);
-          t = fmaf(0.5f, h4.z + l4.z, x4.z); d2 = fmaf(t, t, d2);
-          t = fmaf(0.5f, h4.w + l4.w, x4.w); d2 = fmaf(t, t, d2);
-        }
+      for (int t = 0; t < 4; ++t) {
+        if (tb[t] < best || (tb[t] == best && tj[t] < bj)) { second = fminf(second, best); best = tb[t]; bj = tj[t]; }
+        else second = fminf(second, tb[t]);
+        second = fminf(second, ts[t]);
       }
+      if (bj == 0x7fffffff) bj = 0;
       const long long row = tile * BM + r;
       const bool valid = row < a.n;
-      if (valid) {
-        const float outv = a.squared ? d2 : sqrtf(d2);
-        inertia_acc += (double)outv;
-        if (a.labels) a.labels[row] = bj;
-        if (a.min_out) reinterpret_cast<float*>(a.min_out)[row] = outv;
+      // near-tie: the 3xTF32 margin is within the rounding bound -> float64 re-check by warp 3
+      const bool flagged = valid && a.tau > 0.f && a.k > 1 && !(second - best > a.tau * (xn + cnmax));
+      if (valid && !flagged && a.labels) a.labels[row] = bj;
+      if (flagged) {
+        // deferred: tc_recheck_kernel decides this row in float64 and adds its M-step contribution
+        const int slot = atomicAdd(a.defer_cnt, 1);
+        a.defer_idx[slot] = (int)row;
       }
-      if (MSTEP) {
+      {
         const int lb = (int)(it & 1);
         mbar_wait(BAR(BAR_LAB_EMPTY + lb), (uint32_t)(((it >> 1) & 1) ^ 1));
-        lab_s[lb * BM + r] = valid ? bj : -1;
+        lab_s[lb * BM + r] = (valid && !flagged) ? bj : -1;
         mbar_arrive(BAR(BAR_LAB_FULL + lb));       // release semantics order the smem store
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(BAR_X_EMPTY + stage));
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, o);
-    if (lane == 0) red_s[q4] = inertia_acc;
   } else if (warp >= 8) {
-    // =========================== M-step ===========================
-    if (MSTEP) {
-      const int wm = warp - 8;
-      float acc[32][2];
+    // =========================== distance + M-step warps ===========================
+    // Warp wm owns the rows whose label c satisfies c % 8 == wm.  Lane l holds features l and l+32 of
+    // the row (conflict-free reads of the swizzled tile): (a) the winning distance is re-evaluated
+    // exactly in fp32 direct form sum (x-c)^2 with c = -(bhi+blo)/2 read from the resident B tiles,
+    // (b) [MSTEP] the row is added to the register-resident sums of cluster c.
+    const int wm = warp - 8;
+    float acc[32][2];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
-      int cnt = 0;
-      const bool two = KB > 1;
-      for (long long it = 0; it < my_tiles; ++it) {
-        const int stage = (int)(it % NST);
-        const int lb = (int)(it & 1);
-        mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
-        mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
-        const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
-        for (int base = 0; base < BM; base += 32) {
-          const int ml = lab_s[lb * BM + base + lane];
-          unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int c = __shfl_sync(0xffffffffu, ml, b);
+    for (int j = 0; j < 32; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+    int cnt = 0;
+    double inertia_acc = 0.0;
+    const bool two = KB > 1;
+    mbar_wait(BAR(BAR_B_FULL), 0);
+#pragma unroll 1
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const int stage = (int)(it % NST);
+      const int lb = (int)(it & 1);
+      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+      mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+#pragma unroll 1
+      for (int base = 0; base < BM; base += 32) {
+        const int ml = lab_s[lb * BM + base + lane];
+        unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
+#pragma unroll 1
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int c = __shfl_sync(0xffffffffu, ml, b);
+          const int row = base + b;
+          const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
+          const float x0 = *reinterpret_cast<const float*>(xs + ro);
+          const float x1 = two ? *reinterpret_cast<const float*>(xs + KBLK_BYTES + ro) : 0.f;
+          if (WANT_DIST) {
+            const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2));
+            float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +
+                                 *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);
+            float s2 = t * t;
+            if (two) {
+              const uint32_t c1 = co + (uint32_t)NP * 128u;
+              t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +
+                             *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);
+              s2 = fmaf(t, t, s2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) {
+              const float outv = a.squared ? s2 : sqrtf(s2);
+              inertia_acc += (double)outv;
+              if (a.min_out) reinterpret_cast<float*>(a.min_out)[tile * BM + row] = outv;
+            }
+          }
+          if (MSTEP) {
             const int cl = c >> 3;
-            const int row = base + b;
-            const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
-            const float x0 = *reinterpret_cast<const float*>(xs + ro);
-            const float x1 = two ? *reinterpret_cast<const float*>(xs + KBLK_BYTES + ro) : 0.f;
             switch (cl) {
               ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)
               ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)
@@ -400,12 +445,15 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
             cnt += (lane == cl) ? 1 : 0;
           }
         }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
-          mbar_arrive(BAR(BAR_X_EMPTY + stage));
-        }
       }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+        mbar_arrive(BAR(BAR_X_EMPTY + stage));
+      }
+    }
+    if (lane == 0) red_s[wm] = inertia_acc;
+    if (MSTEP) {
       // flush the register-resident sums: cluster c = wm + 8 j, features lane and lane + 32
       float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d;
 #pragma unroll
@@ -425,11 +473,86 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0) a.pin[blockIdx.x] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
+  if (tid == 0) {
+    double t = red_s[8];
+    for (int w = 0; w < 8; ++w) t += red_s[w];
+    a.pin[blockIdx.x] = t;
+  }
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
 #undef BAR
+}
+
+// ------------------------------------------------------------------------------------------
+// Deferred float64 re-check.  Rows whose 3xTF32 best/second margin was inside the rounding bound
+// were left out of the fused kernel's outputs and M-step; here they are decided exactly:
+// d2_j = sum_i (x_i - c_ji)^2 in float64 against the float64 centres (transposed in shared memory so
+// that thread j <-> centre j reads are conflict-free), lowest index on exact ties.  Their labels,
+// distances and M-step contributions are then added (float64 atomics: order-insensitive to ~1e-16).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_recheck_kernel(ChunkArgs a, bool mstep, double* sums, unsigned long long* counts, double* dist_sum) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int cnt = *a.defer_cnt;
+  if ((int)blockIdx.x >= cnt) return;
+  const int k = a.k, d = a.d, tid = threadIdx.x;
+  const int kpad = (k + 31) / 32 * 32 + 1;                 // odd pitch: conflict-free transpose writes
+  double* cT = reinterpret_cast<double*>(smem);             // [d][kpad]
+  float* xrow = reinterpret_cast<float*>(smem + (size_t)d * kpad * 8);   // [d]
+  double* wd = reinterpret_cast<double*>(xrow + ((d + 3) & ~3));         // [8]
+  int* wj = reinterpret_cast<int*>(wd + 8);                               // [8]
+  const double* gC64 = reinterpret_cast<const double*>(a.pack + a.L.off_c64);
+  for (int e = tid; e < k * d; e += 256) { const int j = e / d, i = e - j * d; cT[i * kpad + j] = gC64[e]; }
+  const float* X = reinterpret_cast<const float*>(a.X);
+  for (int f = blockIdx.x; f < cnt; f += gridDim.x) {
+    const long long row = a.defer_idx[f];
+    __syncthreads();
+    for (int i = tid; i < d; i += 256) xrow[i] = X[row * a.ldx + i];
+    __syncthreads();
+    double bd = CUDART_INF; int bj = 0x7fffffff;
+    for (int j = tid; j < k; j += 256) {
+      double s0 = 0.0, s1 = 0.0;
+      int i = 0;
+      for (; i + 1 < d; i += 2) {
+        const double d0 = (double)xrow[i] - cT[i * kpad + j];
+        const double d1 = (double)xrow[i + 1] - cT[(i + 1) * kpad + j];
+        s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
+      }
+      if (i < d) { const double d0 = (double)xrow[i] - cT[i * kpad + j]; s0 = fma(d0, d0, s0); }
+      const double sdist = s0 + s1;
+      if (sdist < bd) { bd = sdist; bj = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+    }
+    if ((tid & 31) == 0) { wd[tid >> 5] = bd; wj[tid >> 5] = bj; }
+    __syncthreads();
+    double fd = wd[0]; int fj = wj[0];
+    for (int w = 1; w < 8; ++w) if (wd[w] < fd || (wd[w] == fd && wj[w] < fj)) { fd = wd[w]; fj = wj[w]; }
+    if (tid == 0) {
+      const double outv = a.squared ? fd : sqrt(fd);
+      if (a.labels) a.labels[row] = fj;
+      if (a.min_out) reinterpret_cast<float*>(a.min_out)[row] = (float)outv;
+      if (dist_sum) atomicAdd(dist_sum, outv);
+      if (mstep) atomicAdd(counts + fj, 1ull);
+    }
+    if (mstep) for (int i = tid; i < d; i += 256) atomicAdd(sums + (size_t)fj * d + i, (double)xrow[i]);
+  }
+}
+
+static int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t s) {
+  const int kpad = (a.k + 31) / 32 * 32 + 1;
+  const size_t smem = (size_t)a.d * kpad * 8 + (size_t)((a.d + 3) & ~3) * 4 + 8 * 8 + 8 * 4 + 16;
+  if (smem > 227 * 1024) return BKM_EUNSUPPORTED;
+  BKM_CUDA_TRY(cudaFuncSetAttribute(tc_recheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_recheck_kernel<<<sm_count, 256, smem, s>>>(a, mstep, a.out_sums, (unsigned long long*)a.out_counts, a.out_dist_sum);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -482,7 +605,8 @@ static bool make_cfg(int d, int k, TcCfg* c) {
     c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;
     c->off_cn = o; o += (uint32_t)c->NP * 4;
     c->off_lab = o; o += 2 * BM * 4;
-    c->off_red = o; o += 32;
+    c->off_flist = o;
+    c->off_red = o; o += 72;
     c->off_bar = o; o += BAR_COUNT * 8;
     c->off_tptr = o; o += 16;
     c->total = o;
@@ -507,12 +631,22 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
   if (grid < 1) grid = 1;
   *grid_out = grid;
-  if (mstep) {
-    BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.total));
-    tc_chunk_kernel<true><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);
-  } else {
-    BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.total));
-    tc_chunk_kernel<false><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);
+  const bool want_dist = !mstep || a.min_out != nullptr || a.want_sum;
+  BKM_CUDA_TRY(cudaMemsetAsync(a.defer_cnt, 0, sizeof(int), s));
+#define TC_LAUNCH(M, W)                                                                                       \
+  {                                                                                                           \
+    BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)cfg.total));                                                       \
+    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);                  \
+  }
+  if (mstep) { if (want_dist) TC_LAUNCH(true, true) else TC_LAUNCH(true, false) }
+  else TC_LAUNCH(false, true)
+#undef TC_LAUNCH
+  note_launch(2);
+  BKM_CUDA_TRY(cudaGetLastError());
+  if (a.tau > 0.f && a.k > 1) {
+    int rc2 = launch_tc_recheck(a, mstep, sm_count, s);
+    if (rc2) return rc2;
   }
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());

@@ -78,7 +78,9 @@ class CudaBackend(object):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
-        self.flags = int(flags)
+        import os
+
+        self.flags = int(flags) | int(os.environ.get("BKM_FLAGS", "0"))   # BKM_FLAGS: debugging aid
         self._ws = {}
 
     # -- helpers -------------------------------------------------------------------------
@@ -89,13 +91,14 @@ class CudaBackend(object):
     def _ptr(t):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
-    def _workspace(self, d, k, dtype):
+    def _workspace(self, n, d, k, dtype):
+        """Scratch for one chunk call (per-CTA partials + the deferred-row list, 4 bytes per row)."""
         key = (d, k, dtype)
         ws = self._ws.get(key)
-        if ws is None:
-            nbytes = ctypes.c_size_t(0)
-            _lib.check(self.lib.bkm_workspace_bytes(0, d, k, _DT_CODE[dtype], ctypes.byref(nbytes)),
-                       "bkm_workspace_bytes")
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.bkm_workspace_bytes(int(n), d, k, _DT_CODE[dtype], ctypes.byref(nbytes)),
+                   "bkm_workspace_bytes")
+        if ws is None or ws.numel() < nbytes.value:
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
@@ -146,7 +149,7 @@ class CudaBackend(object):
 
     def lloyd_chunk(self, x, pack, k, labels, min_d2, sums, counts, inertia):
         n, d = x.shape
-        ws = self._workspace(d, k, x.dtype)
+        ws = self._workspace(n, d, k, x.dtype)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bkm_lloyd_chunk(
                 self._ptr(x), n, d, x.stride(0) if n else d, _DT_CODE[x.dtype], self._ptr(pack), k,
@@ -156,7 +159,7 @@ class CudaBackend(object):
 
     def assign_chunk(self, x, pack, k, labels, min_dist, squared, dist_sum):
         n, d = x.shape
-        ws = self._workspace(d, k, x.dtype)
+        ws = self._workspace(n, d, k, x.dtype)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bkm_assign_chunk(
                 self._ptr(x), n, d, x.stride(0) if n else d, _DT_CODE[x.dtype], self._ptr(pack), k,
