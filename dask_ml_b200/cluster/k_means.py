@@ -422,7 +422,8 @@ class LloydState(object):
         self.X, self.be = X, be
         k, d = centers.shape
         self.k, self.d = int(k), int(d)
-        self.C = torch.as_tensor(np.ascontiguousarray(centers, dtype=np.float64)).to(be.device)
+        # private copy: the state is updated in place and must never alias the caller's `init`
+        self.C = torch.from_numpy(np.array(centers, dtype=np.float64, order="C", copy=True)).to(be.device)
         self.C_new = be.empty((k, d), torch.float64)
         # one buffer so that the per-iteration collective is a single all-reduce
         self.red = be.zeros((k * d + k + 1,), torch.float64)

@@ -78,6 +78,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 24)) __trap();     // a pipeline bug must fail, not hang the GPU
   }
 }
+// Long waits (a whole pipeline stage away): poll with back-off so that the poller does not steal
+// issue slots from the warps doing the work on the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) __nanosleep(128);
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -204,7 +221,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         const long long tile = blockIdx.x + it * gridDim.x;
         const int stage = (int)(it % NST);
         const uint32_t ph = (uint32_t)((it / NST) & 1);
-        mbar_wait(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
+        mbar_wait_sleep(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
         mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
@@ -285,9 +302,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
             xn4[i] = fmaf(e[i], e[i], xn4[i]);
             const float hi = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);
             const float lo = e[i] - hi;            // exact: the 13 low mantissa bits
-            uint32_t lo_t;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_t) : "f"(lo));
-            v[q * 4 + i] = lo_t;
+            v[q * 4 + i] = __float_as_uint(lo);
           }
         }
         const uint32_t taddr = tmem + lane_addr + 256u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u;
@@ -396,8 +411,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       const long long tile = blockIdx.x + it * gridDim.x;
       const int stage = (int)(it % NST);
       const int lb = (int)(it & 1);
-      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
-      mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+      if (wm == 0) {
+        mbar_wait_sleep(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+        mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+      }
+      named_bar_sync(1, 256);            // the other 7 warps park here (no polling, no issue slots)
       const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
 #pragma unroll 1
       for (int base = 0; base < BM; base += 32) {

@@ -1,0 +1,207 @@
+"""Host-side logic without a GPU: the C-ABI library loads and exports every declared symbol; the
+estimator's validation / error contract; the Lloyd control flow (reference quirks Q1-Q6) and the
+k-means|| bookkeeping driven through a TEST-ONLY checker backend built on the CPU oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import sklearn.datasets
+from sklearn.cluster import KMeans as SKKMeans, kmeans_plusplus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture
+def cpu_engine(monkeypatch, oracle):
+    from dask_ml_b200.cluster import k_means as km
+    from oracle_backend import OracleBackend
+
+    monkeypatch.setattr(km, "_BACKEND_FACTORY", OracleBackend)
+    return km
+
+
+# ------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    """include/bkm_b200.h vs the built .so vs the ctypes table: all three must agree (no compute calls)."""
+    from dask_ml_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "bkm_b200.h")).read()
+    declared = set(re.findall(r"\b(bkm_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.bkm_version() == 100
+    assert lib.bkm_error_string(-3) == b"shape not supported by any kernel"
+    out = ctypes.c_size_t(0)
+    assert lib.bkm_centers_pack_bytes(256, 64, 0, ctypes.byref(out)) == 0 and out.value > 256 * 64 * 4
+    assert lib.bkm_workspace_bytes(1000, 64, 256, 0, ctypes.byref(out)) == 0 and out.value > 0
+    assert lib.bkm_workspace_bytes(1000, 64, 256, 7, ctypes.byref(out)) == -2          # BKM_EDTYPE
+    assert lib.bkm_kernel_family(64, 256, 0, 0) == 1      # tcgen05 path
+    assert lib.bkm_kernel_family(41, 100, 0, 0) == 0      # CUDA-core path (row pitch not 16-byte aligned)
+    assert lib.bkm_kernel_family(64, 256, 1, 0) == 0      # float64 -> CUDA cores
+    assert lib.bkm_kernel_family(64, 1024, 0, 2) == -3    # FORCE_TC on an unsupported shape
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dask_ml_b200.cluster import KMeans
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        KMeans(3).fit(np.random.rand(50, 2))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under dask_ml_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dask_ml_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "kmeans_oracle" not in src and "oracle_c" not in src and "from oracle" not in src, f
+
+
+# ------------------------------------------------------------------------------------------ ChunkedArray
+def test_chunked_array_protocol():
+    from dask_ml_b200 import ChunkedArray
+
+    X = np.arange(70.0).reshape(35, 2)
+    c = ChunkedArray.from_array(X, 10)
+    assert c.chunks == ((10, 10, 10, 5), (2,)) and c.shape == (35, 2) and c.dtype == np.float64
+    assert c.numblocks == (4, 1) and len(c) == 35
+    np.testing.assert_array_equal(c.compute(), X)
+    np.testing.assert_array_equal(np.asarray(c), X)
+    np.testing.assert_array_equal(c.rows([34, 0, 12]), X[[34, 0, 12]])
+    assert c.astype("f4").dtype == np.float32
+    with pytest.raises(ValueError):
+        ChunkedArray([np.zeros((3, 2)), np.zeros((3, 3))])
+
+
+# ------------------------------------------------------------------------------------------ estimator
+def test_fit_given_init(cpu_engine):
+    """reference tests/test_kmeans.py:87-98 through the estimator + host loop."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    X_, _ = sklearn.datasets.make_blobs(n_samples=1000, n_features=4, random_state=1)
+    init, _ = kmeans_plusplus(X_, 3, random_state=np.random.RandomState(0))
+    dkkm = KMeans(3, init=init, random_state=0).fit(ChunkedArray.from_array(X_, 500))
+    skkm = SKKMeans(3, init=init, random_state=0, n_init=1).fit(X_)
+    np.testing.assert_allclose(dkkm.inertia_, skkm.inertia_)
+    np.testing.assert_array_equal(dkkm.labels_.compute(), skkm.labels_)
+    assert dkkm.labels_.dtype == np.int32 and isinstance(dkkm.inertia_, np.float64)
+    assert dkkm.cluster_centers_.dtype == X_.dtype and dkkm.n_iter_ == 2
+
+
+def test_host_loop_equals_oracle_on_all_branches(cpu_engine, oracle):
+    """Same control flow as k_means.py:499-569 on: converged (<=1e-7), tol break with re-label, max_iter."""
+    from dask_ml_b200.cluster import KMeans
+
+    centers = np.array([[-7, -7], [0, 0], [7, 7]])
+    Xs, _ = oracle.make_blobs(cluster_std=0.1, centers=centers, chunks=50, random_state=0)
+    X = np.concatenate(Xs)
+    init = centers.astype(np.float64)
+    for tol, max_iter in ((1e-4, 300), (0.5, 300), (0.0, 3), (0.0, 1), (1e-12, 300)):
+        km = KMeans(3, init=init, tol=tol, max_iter=max_iter).fit(X)
+        lab, inertia, C, n_iter = oracle.kmeans_single_lloyd(Xs, 3, init=init, tol=tol, max_iter=max_iter)
+        assert km.n_iter_ == n_iter
+        np.testing.assert_allclose(km.inertia_, inertia, rtol=1e-12)
+        np.testing.assert_allclose(km.cluster_centers_, C, rtol=1e-13, atol=1e-15)
+        np.testing.assert_array_equal(km.labels_.compute(), np.concatenate(lab))
+
+
+def test_predict_transform_and_dtypes(cpu_engine):
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    X = np.random.RandomState(0).uniform(size=(100, 2))
+    X2 = X.astype("f4")
+    for xx, yy in [(X, X), (X2, X2), (X, X2), (X2, X)]:
+        a = KMeans(random_state=0).fit(ChunkedArray.from_array(xx, 50))
+        b = SKKMeans(n_init=1, random_state=0).fit(xx)
+        assert a.cluster_centers_.dtype == b.cluster_centers_.dtype
+        assert a.labels_.dtype == b.labels_.dtype
+        assert a.transform(xx).dtype == b.transform(xx).dtype
+        assert a.transform(yy).dtype == b.transform(yy).dtype
+        p = a.predict(xx)
+        assert p.dtype == np.int32 and p.shape == (100,)
+        d = ((xx[:, None, :].astype(float) - a.cluster_centers_[None].astype(float)) ** 2).sum(-1)
+        np.testing.assert_array_equal(p.compute(), d.argmin(1))
+
+
+def test_error_contract(cpu_engine):
+    """reference tests/test_kmeans.py:45-51,131-147,162-166 + NaN/inf (k_means.py:179-185)."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans, k_means as km_mod
+
+    km = KMeans()
+    with pytest.raises(ValueError):
+        km.fit(np.array([]).reshape(0, 1))
+    with pytest.raises(ValueError):
+        km.fit(np.array([]).reshape(1, 0))
+    X = np.random.RandomState(0).uniform(size=(100, 3))
+    Xc = ChunkedArray.from_array(X, 25)
+    with pytest.raises(ValueError):
+        km_mod.k_init(Xc, 3, X[:2])
+    with pytest.raises(ValueError):
+        km_mod.k_init(Xc, 2, X[:2, :-1])
+    with pytest.raises(ValueError):
+        km_mod.k_init(Xc, 2, "invalid")
+    with pytest.raises(TypeError):
+        km_mod.k_init(Xc, 2, 2)
+    X[7, 1] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        km.fit(ChunkedArray.from_array(X, 25))
+
+    class FakeDaskDataFrame(object):
+        pass
+    FakeDaskDataFrame.__module__ = "dask.dataframe.core"
+    with pytest.raises(TypeError):
+        km.fit(FakeDaskDataFrame())
+
+
+def test_inputs_and_too_small(cpu_engine):
+    """reference tests/test_kmeans.py:39-42,149-160."""
+    import pandas as pd
+
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    rng = np.random.RandomState(0)
+    KMeans(random_state=0).fit(ChunkedArray.from_array(rng.uniform(size=(20, 2)), 10))
+    for X in (rng.uniform(size=(100, 4)), ChunkedArray.from_array(rng.uniform(size=(100, 4)), (10, 4)),
+              pd.DataFrame(rng.uniform(size=(100, 4))), rng.randint(0, 9, size=(100, 4)).astype(np.int32)):
+        km = KMeans(n_clusters=3, random_state=0).fit(X)
+        assert km.transform(X).shape == (100, 3)
+
+
+def test_sklearn_params_protocol():
+    from sklearn.base import clone
+
+    from dask_ml_b200.cluster import KMeans
+
+    km = KMeans(n_clusters=5, init="random", tol=1e-3, n_jobs=4, algorithm="elkan")
+    p = km.get_params()
+    assert p["n_clusters"] == 5 and p["oversampling_factor"] == 2 and p["precompute_distances"] == "auto"
+    assert clone(km).get_params() == p
+    km.set_params(max_iter=7)
+    assert km.max_iter == 7
+
+
+def test_kmeans_parallel_init_is_chunking_invariant(cpu_engine, oracle):
+    """The Philox draw is keyed by the global row index, so k-means|| picks the same candidates whatever
+    the chunking; and it matches the oracle's init_scalable driven by the same stream."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import k_means as km_mod
+
+    rng = np.random.RandomState(3)
+    cent = rng.uniform(-20, 20, size=(6, 5))
+    X = cent[rng.randint(0, 6, size=3000)] + 0.3 * rng.standard_normal((3000, 5))
+    a = km_mod.k_init(ChunkedArray.from_array(X, 3000), 6, "k-means||", random_state=5, oversampling_factor=8)
+    b = km_mod.k_init(ChunkedArray.from_array(X, 700), 6, "k-means||", random_state=5, oversampling_factor=8)
+    np.testing.assert_allclose(a, b, rtol=1e-12)
+    assert a.shape == (6, 5)
