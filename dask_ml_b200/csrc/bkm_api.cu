@@ -4,6 +4,8 @@
 #include <math.h>
 
 namespace bkm {
+unsigned int tc_abort_code();
+void tc_abort_detail(unsigned int* out64);
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s);
 int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
                     double* shift, int k, int d, cudaStream_t s);
@@ -213,5 +215,8 @@ int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, 
 }
 
 int64_t bkm_launch_count(void) { return (int64_t)g_launches; }
+
+unsigned int bkm_debug_abort_code(void) { return bkm::tc_abort_code(); }
+void bkm_debug_abort_detail(unsigned int* out64_host) { bkm::tc_abort_detail(out64_host); }
 
 }  // extern "C"

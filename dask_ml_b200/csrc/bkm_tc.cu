@@ -20,9 +20,9 @@
 //     scatter-added into REGISTER-resident per-CTA sums: warp w owns clusters {w, w+8, ...},
 //     lane l owns features {l, l+32}; no atomics, no second read of X from HBM.
 //
-// Warp roles (512 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle
-//                           4-7 Xlo converter + epilogue (thread == row == TMEM lane)
-//                           8-15 M-step
+// Warp roles (640 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle
+//                           4-7 and 8-11 Xlo converter + epilogue, alternate tiles (thread == row == TMEM lane)
+//                           12-19 distance + M-step
 #include "bkm_common.cuh"
 #include <cuda.h>
 #include <math_constants.h>
@@ -30,7 +30,7 @@
 namespace bkm {
 
 static const int BM = 128;           // rows per tile
-static const int TC_THREADS = 512;
+static const int TC_THREADS = 640;
 static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
 
 struct TcCfg {
@@ -47,12 +47,12 @@ enum {
   BAR_B_FULL = 0,
   BAR_X_FULL = 1,       // [NST<=4]
   BAR_X_EMPTY = 5,      // [4]
-  BAR_ACC_FULL = 9,     // [2]
-  BAR_ACC_EMPTY = 11,   // [2]
-  BAR_XLO_FULL = 13,    // [2]
-  BAR_LAB_FULL = 15,    // [2]
-  BAR_LAB_EMPTY = 17,   // [2]
-  BAR_COUNT = 19
+  BAR_ACC_FULL = 9,     // [set 2][buf 2]  one barrier per (epilogue warp set, accumulator buffer): every
+  BAR_ACC_EMPTY = 13,   // [set 2][buf 2]  waiter then observes consecutive phases (no parity aliasing)
+  BAR_XLO_FULL = 17,    // [2]
+  BAR_LAB_FULL = 19,    // [2]
+  BAR_LAB_EMPTY = 21,   // [2]
+  BAR_COUNT = 23
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -67,6 +67,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// A pipeline bug must fail, not hang the GPU: a wait that times out records (barrier offset, parity,
+// warp) in g_tc_abort and returns; every later wait returns at once, the kernel drains with garbage and
+// the host reports the code (bkm_debug_abort_code).
+__device__ unsigned int g_tc_abort = 0;
+__device__ unsigned int g_tc_dbg[64];     // per-warp abort code of the first CTA that aborts (debug)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
@@ -75,7 +80,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > (1u << 24)) __trap();     // a pipeline bug must fail, not hang the GPU
+    if (spin > (1u << 22) || ((spin & 1023) == 1023 && *(volatile unsigned int*)&g_tc_abort)) {
+      atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
+      if (spin > 2048 && (threadIdx.x & 31) == 0) g_tc_dbg[threadIdx.x >> 5] = 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | blockIdx.x;
+      return;
+    }
   }
 }
 // Long waits (a whole pipeline stage away): poll with back-off so that the poller does not steal
@@ -89,7 +98,10 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (!done) __nanosleep(128);
-    if (spin > (1u << 22)) __trap();
+    if (spin > (1u << 20) || ((spin & 255) == 255 && *(volatile unsigned int*)&g_tc_abort)) {
+      atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
+      return;
+    }
   }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -99,6 +111,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));     // FMNMX3 on sm_100
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -185,9 +207,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       mbar_init(BAR(BAR_X_FULL + s), 1);
       mbar_init(BAR(BAR_X_EMPTY + s), 8);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
       mbar_init(BAR(BAR_ACC_EMPTY + b), 128);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(BAR_XLO_FULL + b), 128);
       mbar_init(BAR(BAR_LAB_FULL + b), 128);
       mbar_init(BAR(BAR_LAB_EMPTY + b), 8);
@@ -230,155 +254,212 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      mbar_wait(BAR(BAR_B_FULL), 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (long long it = 0; it < my_tiles; ++it) {
-        const int stage = (int)(it % NST);
-        const uint32_t ph = (uint32_t)((it / NST) & 1);
-        const uint32_t xs = s_x + stage * stage_bytes;
-        const uint32_t xlo_t = tmem + 256u + (uint32_t)(it & 1) * 64u;
-        mbar_wait(BAR(BAR_X_FULL + stage), ph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int u = 0; u < U; ++u) {
-          const long long g = it * U + u;
-          const int buf = (int)(g & 1);
-          mbar_wait(BAR(BAR_ACC_EMPTY + buf), (uint32_t)(((g >> 1) & 1) ^ 1));
-          tc_fence_after();
-          const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
-          const uint32_t rowoff = u == 0 ? 0u : (uint32_t)cfg.NU0 * 128u;
-          const uint32_t idesc = make_idesc(ncols);
-          const uint32_t d_t = tmem + (uint32_t)buf * 128u;
-          // pass 1: Xhi . Bhi   (A = raw fp32 tile; the tensor core reads the tf32 part)
-#pragma unroll 1
-          for (int s = 0; s < KS; ++s) {
-            const uint32_t ko = (uint32_t)(s >> 2) , ks = (uint32_t)(s & 3) * 32u;
-            mma_tf32_ss(d_t, make_desc(xs + ko * KBLK_BYTES + ks),
-                        make_desc(s_bhi + ko * NP * 128u + rowoff + ks), idesc, s > 0 ? 1u : 0u);
-          }
-          // pass 2: Xhi . Blo
-#pragma unroll 1
-          for (int s = 0; s < KS; ++s) {
-            const uint32_t ko = (uint32_t)(s >> 2), ks = (uint32_t)(s & 3) * 32u;
-            mma_tf32_ss(d_t, make_desc(xs + ko * KBLK_BYTES + ks),
-                        make_desc(s_blo + ko * NP * 128u + rowoff + ks), idesc, 1u);
-          }
-          if (u == 0) {
-            mbar_wait(BAR(BAR_XLO_FULL + (it & 1)), (uint32_t)((it >> 1) & 1));
-            tc_fence_after();
-          }
-          // pass 3: Xlo . Bhi   (A from TMEM)
-#pragma unroll 1
-          for (int s = 0; s < KS; ++s) {
-            const uint32_t ko = (uint32_t)(s >> 2), ks = (uint32_t)(s & 3) * 32u;
-            mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, make_desc(s_bhi + ko * NP * 128u + rowoff + ks), idesc, 1u);
-          }
-          tc_commit(BAR(BAR_ACC_FULL + buf));
-        }
-      }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // =========================== Xlo converter + epilogue ===========================
-    const int q4 = warp - 4;
-    const int r = q4 * 32 + lane;                 // row in tile == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    float xn_next = 0.f;
-    auto convert = [&](long long it) {
-      const int stage = (int)(it % NST);
-      const uint32_t ph = (uint32_t)((it / NST) & 1);
-      mbar_wait(BAR(BAR_X_FULL + stage), ph);
-      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
-      float xn4[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int kb = 0; kb < KB; ++kb) {
-        uint32_t v[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + sw_chunk(r, q));
-          const float e[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            xn4[i] = fmaf(e[i], e[i], xn4[i]);
-            const float hi = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);
-            const float lo = e[i] - hi;            // exact: the 13 low mantissa bits
-            v[q * 4 + i] = __float_as_uint(lo);
-          }
-        }
-        const uint32_t taddr = tmem + lane_addr + 256u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u;
-        TC_ST32(taddr, v);
-      }
-      xn_next = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
-    };
-
-    mbar_wait(BAR(BAR_B_FULL), 0);              // B tiles are read below through the generic proxy
-    const float cnmax = (float)reinterpret_cast<const PackHeader*>(a.pack)->cn_max;
-    if (my_tiles > 0) convert(0);
+    // The whole warp runs this loop converged (all addresses / descriptors are warp-uniform and live
+    // in uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
+    const bool leader = elect_one();      // one lane issues every tcgen05.mma / commit (same thread: ordered)
+    mbar_wait(BAR(BAR_B_FULL), 0);
+    tc_fence_after();
+    const uint64_t dflags = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint32_t bblk = (uint32_t)NP * 128u;          // bytes of one K-block of a B tile
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
-      const float xn = xn_next;
-      if (it + 1 < my_tiles) convert(it + 1);
+      const int stage = (int)(it % NST);
+      const uint32_t ph = (uint32_t)((it / NST) & 1);
+      const uint32_t xs = s_x + stage * stage_bytes;
+      const uint32_t xlo_t = tmem + 256u + (uint32_t)(it & 1) * 64u;
+      mbar_wait(BAR(BAR_X_FULL + stage), ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+        const long long g = it * U + u;
+        const int buf = (int)(g & 1);
+        if (g >= 2) {
+          // buffer `buf` was last used by unit g-2: tile pt, consumed by epilogue set pt&1 as that set's
+          // (pt>>1)-th tile
+          const long long pt = (g - 2) / U;
+          mbar_wait(BAR(BAR_ACC_EMPTY + (int)(pt & 1) * 2 + buf), (uint32_t)((pt >> 1) & 1));
+        }
+        tc_fence_after();
+        const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
+        const uint32_t rowoff = u == 0 ? 0u : (uint32_t)cfg.NU0 * 128u;
+        const uint32_t idesc = make_idesc(ncols);
+        const uint32_t d_t = tmem + (uint32_t)buf * 128u;
+        const uint64_t da = dflags | (uint64_t)((xs >> 4) & 0x3FFF);
+        const uint64_t dbh = dflags | (uint64_t)(((s_bhi + rowoff) >> 4) & 0x3FFF);
+        const uint64_t dbl = dflags | (uint64_t)(((s_blo + rowoff) >> 4) & 0x3FFF);
+        // pass 1: Xhi . Bhi (A = raw fp32 tile; the tensor core reads its tf32 part), pass 2: Xhi . Blo
+        if (leader) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s < KS) {
+              const uint32_t ao = (uint32_t)(s >> 2) * (KBLK_BYTES >> 4) + (uint32_t)(s & 3) * 2u;
+              const uint32_t bo = (uint32_t)(s >> 2) * (bblk >> 4) + (uint32_t)(s & 3) * 2u;
+              mma_tf32_ss(d_t, da + ao, dbh + bo, idesc, s > 0 ? 1u : 0u);
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s < KS) {
+              const uint32_t ao = (uint32_t)(s >> 2) * (KBLK_BYTES >> 4) + (uint32_t)(s & 3) * 2u;
+              const uint32_t bo = (uint32_t)(s >> 2) * (bblk >> 4) + (uint32_t)(s & 3) * 2u;
+              mma_tf32_ss(d_t, da + ao, dbl + bo, idesc, 1u);
+            }
+          }
+        }
+        __syncwarp();
+        if (u == 0) {
+          mbar_wait(BAR(BAR_XLO_FULL + (it & 1)), (uint32_t)((it >> 1) & 1));
+          tc_fence_after();
+        }
+        // pass 3: Xlo . Bhi   (A from TMEM)
+        if (leader) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            if (s < KS) {
+              const uint32_t bo = (uint32_t)(s >> 2) * (bblk >> 4) + (uint32_t)(s & 3) * 2u;
+              mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + bo, idesc, 1u);
+            }
+          }
+          tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * 2 + buf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // =========================== Xlo converter + epilogue ===========================
+    // Two warp sets (warps 4-7 and 8-11) take alternate tiles, so each SM sub-partition has two epilogue
+    // warps whose instruction streams interleave.  Thread == row == TMEM lane.
+    const int set = (warp - 4) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const float cnmax = (float)reinterpret_cast<const PackHeader*>(a.pack)->cn_max;
+    uint32_t xoff[8];                              // swizzled 16-byte chunk offsets of this thread's row
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
+    mbar_wait(BAR(BAR_B_FULL), 0);
+#pragma unroll 1
+    for (long long it = set; it < my_tiles; it += 2) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const int stage = (int)(it % NST);
-      // four independent (best, second, argmin) trackers over column classes j % 4 break the
-      // serial min chain; they are merged after the last unit (lowest index wins ties).
-      float tb[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
-      float ts[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
-      int tj[4] = {0, 0, 0, 0};
-#define EPI_PROCESS(V, COLBASE)                                                          \
-  {                                                                                      \
-    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
-      const float cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w};                                  \
-      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                    \
-        const float dist = __uint_as_float(V[j4 * 4 + j]) + cn[j];                       \
-        ts[j] = fminf(ts[j], fmaxf(tb[j], dist));                                        \
-        if (dist < tb[j]) { tb[j] = dist; tj[j] = (COLBASE) + j4 * 4 + j; }              \
-      }                                                                                  \
-    }                                                                                    \
-  }
+      // ---- convert: Xlo = X - tf32(X) -> TMEM, and ||x||^2 ----
+      float xn;
+      {
+        mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+        const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+        float xn4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          uint32_t v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + xoff[q]);
+            const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              xn4[i] = fmaf(e[i], e[i], xn4[i]);
+              const float hi = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);
+              v[q * 4 + i] = __float_as_uint(e[i] - hi);     // exact: the 13 low mantissa bits
+            }
+          }
+          TC_ST32(tmem + lane_addr + 256u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u, v);
+        }
+        xn = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
+      }
+      const float bound = a.tau * (xn + cnmax);
+      // ---- two-pass epilogue per unit ----
+      //  pass 1: m = min_j (S_j + ||c_j||^2)                      (1 FADD + 1/2 FMNMX3 per element)
+      //  pass 2: every element within `bound` of m adds (1 + j/1024) to an accumulator on the FMA pipe:
+      //          exactly one hit  -> acc = 1 + j/1024 : the arg-min, decoded exactly
+      //          two or more hits -> acc >= 2        : near-tie, the row is deferred to float64
+      float um0 = CUDART_INF_F, um1 = CUDART_INF_F, ua0 = 0.f, ua1 = 0.f;
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const long long g = it * U + u;
         const int buf = (int)(g & 1);
         const int nch = (u == 0 ? cfg.NU0 : cfg.NU1) >> 4;
         const int col0 = u == 0 ? 0 : cfg.NU0;
-        mbar_wait(BAR(BAR_ACC_FULL + buf), (uint32_t)((g >> 1) & 1));
+        mbar_wait(BAR(BAR_ACC_FULL + set * 2 + buf), (uint32_t)((it >> 1) & 1));   // this set's (it>>1)-th tile
         tc_fence_after();
         const uint32_t tbase = tmem + lane_addr + (uint32_t)buf * 128u;
         uint32_t v0[16], v1[16];
+        float ma = CUDART_INF_F, mb = CUDART_INF_F;
+#define EPI_MIN(V, COLBASE)                                                              \
+  {                                                                                      \
+    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
+      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
+      const float d0 = __uint_as_float(V[j4 * 4 + 0]) + cn4.x;                           \
+      const float d1 = __uint_as_float(V[j4 * 4 + 1]) + cn4.y;                           \
+      const float d2 = __uint_as_float(V[j4 * 4 + 2]) + cn4.z;                           \
+      const float d3 = __uint_as_float(V[j4 * 4 + 3]) + cn4.w;                           \
+      ma = fmin3(ma, d0, d1);                                                            \
+      mb = fmin3(mb, d2, d3);                                                            \
+    }                                                                                    \
+  }
         TC_LD16(tbase, v0);
 #pragma unroll 1
         for (int c = 0; c < nch; c += 2) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (c + 1 < nch) TC_LD16(tbase + (uint32_t)(c + 1) * 16u, v1);
-          EPI_PROCESS(v0, col0 + c * 16)
+          EPI_MIN(v0, col0 + c * 16)
           if (c + 1 < nch) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (c + 2 < nch) TC_LD16(tbase + (uint32_t)(c + 2) * 16u, v0);
-            EPI_PROCESS(v1, col0 + (c + 1) * 16)
+            EPI_MIN(v1, col0 + (c + 1) * 16)
           }
         }
+#undef EPI_MIN
+        const float m = fminf(ma, mb);
+        const float thr = m + bound;
+        float acc = 0.f, accb = 0.f;
+#define EPI_HIT(V, COLBASE)                                                              \
+  {                                                                                      \
+    float p0 = 0.f, p1 = 0.f;                                                            \
+    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
+      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
+      const float d0 = __uint_as_float(V[j4 * 4 + 0]) + cn4.x;                           \
+      const float d1 = __uint_as_float(V[j4 * 4 + 1]) + cn4.y;                           \
+      const float d2 = __uint_as_float(V[j4 * 4 + 2]) + cn4.z;                           \
+      const float d3 = __uint_as_float(V[j4 * 4 + 3]) + cn4.w;                           \
+      p0 = fmaf(d0 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 0) * 0.0009765625f, p0);   \
+      p1 = fmaf(d1 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 1) * 0.0009765625f, p1);   \
+      p0 = fmaf(d2 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 2) * 0.0009765625f, p0);   \
+      p1 = fmaf(d3 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 3) * 0.0009765625f, p1);   \
+    }                                                                                    \
+    const float p = p0 + p1;                                                             \
+    acc += p;                                                                            \
+    accb += p >= 1.f ? (float)(COLBASE) : 0.f;                                           \
+  }
+        TC_LD16(tbase, v0);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 1 < nch) TC_LD16(tbase + (uint32_t)(c + 1) * 16u, v1);
+          EPI_HIT(v0, col0 + c * 16)
+          if (c + 1 < nch) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c + 2 < nch) TC_LD16(tbase + (uint32_t)(c + 2) * 16u, v0);
+            EPI_HIT(v1, col0 + (c + 1) * 16)
+          }
+        }
+#undef EPI_HIT
         tc_fence_before();
-        mbar_arrive(BAR(BAR_ACC_EMPTY + buf));
+        mbar_arrive(BAR(BAR_ACC_EMPTY + set * 2 + buf));
+        // acc < 2: one hit, (acc - 1) * 1024 = index inside its 16-column chunk, accb = that chunk's base
+        const float dec = acc < 2.f ? accb + (acc - 1.f) * 1024.f : -1.f;
+        if (u == 0) { um0 = m; ua0 = dec; } else { um1 = m; ua1 = dec; }
       }
-#undef EPI_PROCESS
-      float best = CUDART_INF_F, second = CUDART_INF_F;
-      int bj = 0x7fffffff;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (tb[t] < best || (tb[t] == best && tj[t] < bj)) { second = fminf(second, best); best = tb[t]; bj = tj[t]; }
-        else second = fminf(second, tb[t]);
-        second = fminf(second, ts[t]);
-      }
-      if (bj == 0x7fffffff) bj = 0;
+      // winner across units (unit 0 holds the lower indices: it wins exact ties)
+      const bool win1 = um1 < um0;
+      const float mw = win1 ? um1 : um0, mo = win1 ? um0 : um1, uaw = win1 ? ua1 : ua0;
       const long long row = tile * BM + r;
       const bool valid = row < a.n;
-      // near-tie: the 3xTF32 margin is within the rounding bound -> float64 re-check by warp 3
-      const bool flagged = valid && a.tau > 0.f && a.k > 1 && !(second - best > a.tau * (xn + cnmax));
+      const bool tie = uaw < 0.f || !(mo > mw + bound);
+      const int bj = tie ? 0 : (int)(uaw + 0.5f);
+      const bool flagged = valid && tie && a.k > 1;
       if (valid && !flagged && a.labels) a.labels[row] = bj;
       if (flagged) {
         // deferred: tc_recheck_kernel decides this row in float64 and adds its M-step contribution
@@ -392,13 +473,13 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         mbar_arrive(BAR(BAR_LAB_FULL + lb));       // release semantics order the smem store
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // =========================== distance + M-step warps ===========================
     // Warp wm owns the rows whose label c satisfies c % 8 == wm.  Lane l holds features l and l+32 of
     // the row (conflict-free reads of the swizzled tile): (a) the winning distance is re-evaluated
     // exactly in fp32 direct form sum (x-c)^2 with c = -(bhi+blo)/2 read from the resident B tiles,
     // (b) [MSTEP] the row is added to the register-resident sums of cluster c.
-    const int wm = warp - 8;
+    const int wm = warp - 12;
     float acc[32][2];
 #pragma unroll
     for (int j = 0; j < 32; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
@@ -425,7 +506,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         while (m) {
           const int b = __ffs(m) - 1;
           m &= m - 1;
-          const int c = __shfl_sync(0xffffffffu, ml, b);
+          const int c = __shfl_sync(0xffffffffu, ml, b) & 255;
           const int row = base + b;
           const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
           const float x0 = *reinterpret_cast<const float*>(xs + ro);
@@ -604,6 +685,13 @@ static int make_map(CUtensorMap* tm, const void* base, long long rows, int cols,
   return r == CUDA_SUCCESS ? 0 : BKM_EUNSUPPORTED;
 }
 
+unsigned int tc_abort_code() {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(v));
+  return v;
+}
+void tc_abort_detail(unsigned int* out64) { cudaMemcpyFromSymbol(out64, g_tc_dbg, 64 * sizeof(unsigned int)); }
+
 bool tc_supported(int d, int k, int dtype) {
   return dtype == BKM_F32 && d >= 4 && d <= 64 && (d % 4) == 0 && k >= 1 && k <= 256;
 }
@@ -662,7 +750,7 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
 #undef TC_LAUNCH
   note_launch(2);
   BKM_CUDA_TRY(cudaGetLastError());
-  if (a.tau > 0.f && a.k > 1) {
+  if (a.k > 1) {
     int rc2 = launch_tc_recheck(a, mstep, sm_count, s);
     if (rc2) return rc2;
   }

@@ -136,6 +136,11 @@ int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
 /* Number of kernel launches this library has enqueued since load (for bench accounting). */
 int64_t bkm_launch_count(void);
 
+/* Debug: nonzero once a pipeline wait inside the tcgen05 kernel has timed out (the kernel then drains
+ * instead of hanging); encodes barrier / parity / warp.  Synchronises the device. */
+unsigned int bkm_debug_abort_code(void);
+void bkm_debug_abort_detail(unsigned int* out64_host);   /* per-warp wait that timed out (64 words) */
+
 #ifdef __cplusplus
 }
 #endif

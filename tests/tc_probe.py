@@ -24,6 +24,18 @@ for (n, d, k) in shapes:
     sums = be.zeros((k * d,), torch.float64); counts = be.zeros((k,), torch.int64); inertia = be.zeros((1,), torch.float64)
     be.lloyd_chunk(x, pack, k, labels, mind2, sums, counts, inertia)
     torch.cuda.synchronize()
+    code = be.lib.bkm_debug_abort_code()
+    if code:
+        import ctypes
+        det = (ctypes.c_uint * 64)()
+        be.lib.bkm_debug_abort_detail(ctypes.cast(det, ctypes.c_void_p))
+        print("ABORT first=0x%08x" % code)
+        offs = [((v >> 12) & 0xfff) for v in det if v]
+        base = min(offs) if offs else 0
+        for w, v in enumerate(det):
+            if v:
+                print("  warp %2d: bar_off=%d (rel idx %+d) parity=%d cta=%d" % (w, (v >> 12) & 0xfff, (((v >> 12) & 0xfff) - base) // 8, (v >> 8) & 1, v & 0xff))
+        break
     got = labels.cpu().numpy()
     (olab,), (omin,) = ok.pairwise_distances_argmin_min([X], C, metric_kwargs={"squared": True})
     bad = np.nonzero(got != olab)[0]
