@@ -32,6 +32,8 @@ namespace bkm {
 static const int BM = 128;           // rows per tile
 static const int TC_THREADS = 640;
 static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
+static const int MH = 64;                 // rows per M-ring stage (half a tile)
+static const int MKBLK_BYTES = MH * 128;
 
 struct TcCfg {
   int KB;        // 32-float K-blocks per row (1 or 2)
@@ -40,7 +42,7 @@ struct TcCfg {
   int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
   int U;
   int NST;       // X stages
-  uint32_t off_bhi, off_blo, off_x, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
+  uint32_t off_bhi, off_blo, off_x, off_m, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
 };
 
 enum {
@@ -52,7 +54,9 @@ enum {
   BAR_XLO_FULL = 17,    // [2]
   BAR_LAB_FULL = 19,    // [2]
   BAR_LAB_EMPTY = 21,   // [2]
-  BAR_COUNT = 23
+  BAR_M_FULL = 23,      // [2]  M ring: 64-row half tiles re-fetched (L2 hits) for the M-step warps
+  BAR_M_EMPTY = 25,     // [2]
+  BAR_COUNT = 27
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -179,7 +183,8 @@ __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r
 template <bool MSTEP, bool WANT_DIST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
+                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                const __grid_constant__ CUtensorMap tm_xm) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
@@ -202,16 +207,19 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xm));
     mbar_init(BAR(BAR_B_FULL), 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(BAR(BAR_X_FULL + s), 1);
-      mbar_init(BAR(BAR_X_EMPTY + s), 8);
+      mbar_init(BAR(BAR_X_EMPTY + s), 1);
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
       mbar_init(BAR(BAR_ACC_EMPTY + b), 128);
     }
     for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR(BAR_M_FULL + b), 1);
+      mbar_init(BAR(BAR_M_EMPTY + b), 8);
       mbar_init(BAR(BAR_XLO_FULL + b), 128);
       mbar_init(BAR(BAR_LAB_FULL + b), 128);
       mbar_init(BAR(BAR_LAB_EMPTY + b), 8);
@@ -250,6 +258,25 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
                       kb * 32, (int)(tile * BM));
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== TMA producer of the M ring ===========================
+    // Re-fetches every tile as two 64-row halves for the M-step / distance warps.  The same rows were
+    // loaded for the MMA a few microseconds earlier, so these are L2 hits: HBM traffic stays at one read
+    // of X per iteration while the M-step no longer holds the MMA's shared-memory stages.
+    if (lane == 0) {
+      const uint32_t s_m = sbase + cfg.off_m;
+      const uint32_t mbytes = (uint32_t)KB * MKBLK_BYTES;
+#pragma unroll 1
+      for (long long mi = 0; mi < 2 * my_tiles; ++mi) {
+        const long long tile = blockIdx.x + (mi >> 1) * gridDim.x;
+        const int slot = (int)(mi & 1);
+        mbar_wait_sleep(BAR(BAR_M_EMPTY + slot), (uint32_t)(((mi >> 1) & 1) ^ 1));
+        mbar_expect_tx(BAR(BAR_M_FULL + slot), mbytes);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(s_m + slot * mbytes + (uint32_t)kb * MKBLK_BYTES, &tm_xm, BAR(BAR_M_FULL + slot), kb * 32,
+                      (int)(tile * BM + (mi & 1) * MH));
       }
     }
   } else if (warp == 1) {
@@ -321,6 +348,9 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
             }
           }
           tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * 2 + buf));
+          // the smem stage is free once every MMA of this tile has read it (the Xlo converter finished
+          // before pass 3 could start); later consumers (M-step) read their rows from L2 instead
+          if (u == U - 1) tc_commit(BAR(BAR_X_EMPTY + stage));
         }
         __syncwarp();
       }
@@ -487,70 +517,80 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     double inertia_acc = 0.0;
     const bool two = KB > 1;
     mbar_wait(BAR(BAR_B_FULL), 0);
+#define MSTEP_ROW(XA, XB, CC, ROWG)                                                               \
+  {                                                                                               \
+    const int c = (CC);                                                                           \
+    const float x0 = (XA), x1 = (XB);                                                             \
+    if (WANT_DIST) {                                                                              \
+      const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2)); \
+      float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +             \
+                           *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);         \
+      float s2 = t * t;                                                                           \
+      if (two) {                                                                                  \
+        const uint32_t c1 = co + (uint32_t)NP * 128u;                                             \
+        t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +                 \
+                       *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);             \
+        s2 = fmaf(t, t, s2);                                                                      \
+      }                                                                                           \
+      _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o); \
+      if (lane == 0) {                                                                            \
+        const float outv = a.squared ? s2 : sqrtf(s2);                                            \
+        inertia_acc += (double)outv;                                                              \
+        if (a.min_out) reinterpret_cast<float*>(a.min_out)[(ROWG)] = outv;                        \
+      }                                                                                           \
+    }                                                                                             \
+    if (MSTEP) {                                                                                  \
+      const int cl = c >> 3;                                                                      \
+      switch (cl) {                                                                               \
+        ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)       \
+        ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)     \
+        ACC32_CASE(12) ACC32_CASE(13) ACC32_CASE(14) ACC32_CASE(15) ACC32_CASE(16) ACC32_CASE(17) \
+        ACC32_CASE(18) ACC32_CASE(19) ACC32_CASE(20) ACC32_CASE(21) ACC32_CASE(22) ACC32_CASE(23) \
+        ACC32_CASE(24) ACC32_CASE(25) ACC32_CASE(26) ACC32_CASE(27) ACC32_CASE(28) ACC32_CASE(29) \
+        ACC32_CASE(30) ACC32_CASE(31)                                                             \
+        default: break;                                                                           \
+      }                                                                                           \
+      cnt += (lane == cl) ? 1 : 0;                                                                \
+    }                                                                                             \
+  }
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const int stage = (int)(it % NST);
       const int lb = (int)(it & 1);
-      if (wm == 0) {
-        mbar_wait_sleep(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
-        mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
-      }
-      named_bar_sync(1, 256);            // the other 7 warps park here (no polling, no issue slots)
-      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
 #pragma unroll 1
-      for (int base = 0; base < BM; base += 32) {
-        const int ml = lab_s[lb * BM + base + lane];
-        unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
+      for (int h = 0; h < 2; ++h) {
+        const long long mi = it * 2 + h;
+        const int slot = (int)(mi & 1);
+        if (wm == 0) {
+          if (h == 0) mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+          mbar_wait_sleep(BAR(BAR_M_FULL + slot), (uint32_t)((mi >> 1) & 1));
+        }
+        named_bar_sync(1, 256);          // the other 7 warps park here (no polling, no issue slots)
+        const unsigned char* xs = smem + cfg.off_m + slot * (KB * MKBLK_BYTES);
 #pragma unroll 1
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const int c = __shfl_sync(0xffffffffu, ml, b) & 255;
-          const int row = base + b;
-          const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
-          const float x0 = *reinterpret_cast<const float*>(xs + ro);
-          const float x1 = two ? *reinterpret_cast<const float*>(xs + KBLK_BYTES + ro) : 0.f;
-          if (WANT_DIST) {
-            const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2));
-            float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +
-                                 *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);
-            float s2 = t * t;
-            if (two) {
-              const uint32_t c1 = co + (uint32_t)NP * 128u;
-              t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +
-                             *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);
-              s2 = fmaf(t, t, s2);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            if (lane == 0) {
-              const float outv = a.squared ? s2 : sqrtf(s2);
-              inertia_acc += (double)outv;
-              if (a.min_out) reinterpret_cast<float*>(a.min_out)[tile * BM + row] = outv;
-            }
-          }
-          if (MSTEP) {
-            const int cl = c >> 3;
-            switch (cl) {
-              ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)
-              ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)
-              ACC32_CASE(12) ACC32_CASE(13) ACC32_CASE(14) ACC32_CASE(15) ACC32_CASE(16) ACC32_CASE(17)
-              ACC32_CASE(18) ACC32_CASE(19) ACC32_CASE(20) ACC32_CASE(21) ACC32_CASE(22) ACC32_CASE(23)
-              ACC32_CASE(24) ACC32_CASE(25) ACC32_CASE(26) ACC32_CASE(27) ACC32_CASE(28) ACC32_CASE(29)
-              ACC32_CASE(30) ACC32_CASE(31)
-              default: break;
-            }
-            cnt += (lane == cl) ? 1 : 0;
+        for (int base = 0; base < MH; base += 32) {
+          const int ml = lab_s[lb * BM + h * MH + base + lane];
+          unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
+#pragma unroll 1
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int cq = __shfl_sync(0xffffffffu, ml, b) & 255;
+            const int rh = base + b;      // row inside the 64-row half tile
+            const uint32_t ro = (uint32_t)(rh * 128 + (((lane >> 2) ^ (rh & 7)) << 4) + ((lane & 3) << 2));
+            const float xa = *reinterpret_cast<const float*>(xs + ro);
+            const float xb = two ? *reinterpret_cast<const float*>(xs + MKBLK_BYTES + ro) : 0.f;
+            MSTEP_ROW(xa, xb, cq, tile * BM + h * MH + base + b)
           }
         }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
-        mbar_arrive(BAR(BAR_X_EMPTY + stage));
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(BAR(BAR_M_EMPTY + slot));
+          if (h == 1) mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+        }
       }
     }
+#undef MSTEP_ROW
     if (lane == 0) red_s[wm] = inertia_acc;
     if (MSTEP) {
       // flush the register-resident sums: cluster c = wm + 8 j, features lane and lane + 32
@@ -708,7 +748,8 @@ static bool make_cfg(int d, int k, TcCfg* c) {
     c->off_bhi = o; o += bbytes;
     c->off_blo = o; o += bbytes;
     o = (uint32_t)align_up(o, 1024);
-    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;
+    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring (MMA + Xlo converter)
+    c->off_m = o; o += 2u * c->KB * MKBLK_BYTES;                 // M ring (M-step / distance warps)
     c->off_cn = o; o += (uint32_t)c->NP * 4;
     c->off_lab = o; o += 2 * BM * 4;
     c->off_flist = o;
@@ -726,8 +767,10 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
   TcCfg cfg;
   if (!make_cfg(a.d, a.k, &cfg)) return BKM_EUNSUPPORTED;
-  CUtensorMap tm_x, tm_bhi, tm_blo;
+  CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
   int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
+  if (rc) return rc;
+  rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, MH);
   if (rc) return rc;
   rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
   if (rc) return rc;
@@ -743,7 +786,7 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   {                                                                                                           \
     BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                       (int)cfg.total));                                                       \
-    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);                  \
+    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);                  \
   }
   if (mstep) { if (want_dist) TC_LAUNCH(true, true) else TC_LAUNCH(true, false) }
   else TC_LAUNCH(false, true)
