@@ -72,7 +72,22 @@ __global__ void pack_norms_kernel(const double* __restrict__ C, unsigned char* p
         if (L.dtype == BKM_F32) reinterpret_cast<float*>(pack + L.off_cnT)[j] = (float)s;
         else reinterpret_cast<double*>(pack + L.off_cnT)[j] = s;
       }
-      if (L.dtype == BKM_F32) cn32[j] = j < k ? (float)s : CUDART_INF_F;
+      if (L.dtype == BKM_F32) {
+        cn32[j] = j < k ? (float)s : CUDART_INF_F;
+        // ||c_j||^2 as a K=8 tf32 operand row [hi, mid, lo, 0...] (hi+mid+lo == fp32 value exactly) in the
+        // canonical no-swizzle K-major layout: 8-row groups of 256 B = [8 rows x 16 B | 8 rows x 16 B].
+        float* bcn = reinterpret_cast<float*>(pack + L.off_bcn) + (j >> 3) * 64 + (j & 7) * 4;
+        float hi = 3.0e38f, mid = 0.f, lo = 0.f;
+        if (j < k) {
+          const float cf = (float)s;
+          hi = to_tf32_rna(cf);
+          const float r1 = cf - hi;
+          mid = to_tf32_rna(r1);
+          lo = r1 - mid;
+        }
+        bcn[0] = hi; bcn[1] = mid; bcn[2] = lo; bcn[3] = 0.f;
+        bcn[32] = 0.f; bcn[33] = 0.f; bcn[34] = 0.f; bcn[35] = 0.f;
+      }
     }
   }
 }

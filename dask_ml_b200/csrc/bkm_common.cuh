@@ -30,7 +30,7 @@ struct PackLayout {
   int kp;      // k rounded up to a multiple of 16 (UMMA N granularity)
   int dk;      // d rounded up to a multiple of 32 (one 128-byte swizzle atom of fp32 per K-block)
   size_t esz;  // sizeof(T)
-  size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, total;
+  size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, off_bcn, total;
 };
 
 static inline PackLayout pack_layout(int k, int d, int dtype) {
@@ -48,6 +48,7 @@ static inline PackLayout pack_layout(int k, int d, int dtype) {
   L.off_bhi = o;  o = align_up(o + (size_t)L.kp * L.dk * 4, 256);
   L.off_blo = o;  o = align_up(o + (size_t)L.kp * L.dk * 4, 256);
   L.off_cn32 = o; o = align_up(o + (size_t)L.kp * 4, 256);
+  L.off_bcn = o;  o = align_up(o + (size_t)L.kp * 32, 256);   // ||c||^2 as an MMA operand tile (see bkm_tc.cu)
   L.total = o;
   return L;
 }
