@@ -32,9 +32,6 @@ namespace bkm {
 static const int BM = 128;           // rows per tile
 static const int TC_THREADS = 640;
 static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
-static const int MH = 32;                 // rows per M-ring stage (a quarter tile)
-static const int MKBLK_BYTES = MH * 128;
-static const int MST = 3;                 // M-ring stages
 
 struct TcCfg {
   int KB;        // 32-float K-blocks per row (1 or 2)
@@ -43,7 +40,7 @@ struct TcCfg {
   int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
   int U;
   int NST;       // X stages
-  uint32_t off_bhi, off_blo, off_bcn, off_x, off_m, off_cn, off_list, off_lab, off_flist, off_red, off_bar, off_tptr, total;
+  uint32_t off_bhi, off_blo, off_x, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
 };
 
 enum {
@@ -55,9 +52,7 @@ enum {
   BAR_XLO_FULL = 17,    // [2]
   BAR_LAB_FULL = 19,    // [2]
   BAR_LAB_EMPTY = 21,   // [2]
-  BAR_M_FULL = 23,      // [3]  M ring: 32-row quarter tiles re-fetched (L2 hits) for the M-step warps
-  BAR_M_EMPTY = 26,     // [3]
-  BAR_COUNT = 29
+  BAR_COUNT = 23
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -179,17 +174,18 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 // byte offset of 16-byte chunk q (0..7) of row r inside one swizzled K-block
 __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4)); }
 
+#define ACC32_CASE(j) case j: acc[j][0] += x0; acc[j][1] += x1; break;
 
 template <bool MSTEP, bool WANT_DIST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
-                const __grid_constant__ CUtensorMap tm_xm) {
+                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
   if (tid == 0 && (sbase & 1023)) __trap();
   const uint32_t s_bhi = sbase + cfg.off_bhi, s_blo = sbase + cfg.off_blo, s_x = sbase + cfg.off_x;
+  float* cn_s = reinterpret_cast<float*>(smem + cfg.off_cn);
   int* lab_s = reinterpret_cast<int*>(smem + cfg.off_lab);          // [2][BM]
   double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [5]
   const uint32_t bars = sbase + cfg.off_bar;
@@ -206,19 +202,14 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo));
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xm));
     mbar_init(BAR(BAR_B_FULL), 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(BAR(BAR_X_FULL + s), 1);
-      mbar_init(BAR(BAR_X_EMPTY + s), 1);
+      mbar_init(BAR(BAR_X_EMPTY + s), 8);
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
       mbar_init(BAR(BAR_ACC_EMPTY + b), 128);
-    }
-    for (int b = 0; b < MST; ++b) {
-      mbar_init(BAR(BAR_M_FULL + b), 1);
-      mbar_init(BAR(BAR_M_EMPTY + b), 8);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(BAR_XLO_FULL + b), 128);
@@ -233,11 +224,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   {
-    // ||c||^2 operand tile (NP rows x 32 B): plain copy, then make it visible to the tensor core
-    const float4* g = reinterpret_cast<const float4*>(a.pack + a.L.off_bcn);
-    float4* sdst = reinterpret_cast<float4*>(smem + cfg.off_bcn);
-    for (int i = tid; i < NP * 2; i += TC_THREADS) sdst[i] = g[i];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const float* gcn = reinterpret_cast<const float*>(a.pack + a.L.off_cn32);
+    for (int i = tid; i < NP; i += TC_THREADS) cn_s[i] = gcn[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -257,30 +245,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         const long long tile = blockIdx.x + it * gridDim.x;
         const int stage = (int)(it % NST);
         const uint32_t ph = (uint32_t)((it / NST) & 1);
-        mbar_wait(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
+        mbar_wait_sleep(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
         mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
                       kb * 32, (int)(tile * BM));
-      }
-    }
-  } else if (warp == 3) {
-    // =========================== TMA producer of the M ring ===========================
-    // Re-fetches every tile as four 32-row quarters for the M-step / distance warps.  The same rows were
-    // loaded for the MMA a few microseconds earlier, so these are L2 hits: HBM traffic stays at one read
-    // of X per iteration while the M-step no longer holds the MMA's shared-memory stages.
-    if (lane == 0) {
-      const uint32_t s_m = sbase + cfg.off_m;
-      const uint32_t mbytes = (uint32_t)KB * MKBLK_BYTES;
-#pragma unroll 1
-      for (long long mi = 0; mi < 4 * my_tiles; ++mi) {
-        const long long tile = blockIdx.x + (mi >> 2) * gridDim.x;
-        const int slot = (int)(mi % MST);
-        mbar_wait(BAR(BAR_M_EMPTY + slot), (uint32_t)(((mi / MST) & 1) ^ 1));
-        mbar_expect_tx(BAR(BAR_M_FULL + slot), mbytes);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(s_m + slot * mbytes + (uint32_t)kb * MKBLK_BYTES, &tm_xm, BAR(BAR_M_FULL + slot), kb * 32,
-                      (int)(tile * BM + (mi & 3) * MH));
       }
     }
   } else if (warp == 1) {
@@ -292,9 +261,6 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     tc_fence_after();
     const uint64_t dflags = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     const uint32_t bblk = (uint32_t)NP * 128u;          // bytes of one K-block of a B tile
-    // ||c||^2 operand: SWIZZLE_NONE, LBO = 128 B (second 16-byte K chunk), SBO = 256 B (next 8-row group)
-    const uint64_t dcn = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
-                         (uint64_t)(((sbase + cfg.off_bcn) >> 4) & 0x3FFF);
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const int stage = (int)(it % NST);
@@ -354,12 +320,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
               mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + bo, idesc, 1u);
             }
           }
-          // + ||c_j||^2 : A = constant [1,1,1,0,..] rows in TMEM, B = [hi,mid,lo,0,..] rows (no-swizzle K-major)
-          mma_tf32_ts(d_t, tmem + 384u, dcn + (uint64_t)(rowoff >> 6), idesc, 1u);
           tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * 2 + buf));
-          // the smem stage is free once every MMA of this tile has read it (the Xlo converter finished
-          // before pass 3 could start); later consumers (M-step) read their rows from L2 instead
-          if (u == U - 1) tc_commit(BAR(BAR_X_EMPTY + stage));
         }
         __syncwarp();
       }
@@ -377,14 +338,6 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll
     for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
     mbar_wait(BAR(BAR_B_FULL), 0);
-    if (set == 0) {
-      // constant A operand of the ||c||^2 MMA: columns 384..391 = [1,1,1,0,0,0,0,0] in every lane.  Ordered
-      // before the first MMA that uses it by this set's first XLO_FULL arrival (tile 0).
-      const uint32_t one = __float_as_uint(1.0f);
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                   ::"r"(tmem + lane_addr + 384u), "r"(one), "r"(one), "r"(one), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-                   : "memory");
-    }
 #pragma unroll 1
     for (long long it = set; it < my_tiles; it += 2) {
       const long long tile = blockIdx.x + it * gridDim.x;
@@ -418,8 +371,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       }
       const float bound = a.tau * (xn + cnmax);
       // ---- two-pass epilogue per unit ----
-      //  (the accumulator already holds S_j + ||c_j||^2: the norms enter through an extra MMA K-step)
-      //  pass 1: m = min_j acc_j                                   (1/2 FMNMX3 per element)
+      //  pass 1: m = min_j (S_j + ||c_j||^2)                      (1 FADD + 1/2 FMNMX3 per element)
       //  pass 2: every element within `bound` of m adds (1 + j/1024) to an accumulator on the FMA pipe:
       //          exactly one hit  -> acc = 1 + j/1024 : the arg-min, decoded exactly
       //          two or more hits -> acc >= 2        : near-tie, the row is deferred to float64
@@ -438,10 +390,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #define EPI_MIN(V, COLBASE)                                                              \
   {                                                                                      \
     _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float d0 = __uint_as_float(V[j4 * 4 + 0]);                                   \
-      const float d1 = __uint_as_float(V[j4 * 4 + 1]);                                   \
-      const float d2 = __uint_as_float(V[j4 * 4 + 2]);                                   \
-      const float d3 = __uint_as_float(V[j4 * 4 + 3]);                                   \
+      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
+      const float d0 = __uint_as_float(V[j4 * 4 + 0]) + cn4.x;                           \
+      const float d1 = __uint_as_float(V[j4 * 4 + 1]) + cn4.y;                           \
+      const float d2 = __uint_as_float(V[j4 * 4 + 2]) + cn4.z;                           \
+      const float d3 = __uint_as_float(V[j4 * 4 + 3]) + cn4.w;                           \
       ma = fmin3(ma, d0, d1);                                                            \
       mb = fmin3(mb, d2, d3);                                                            \
     }                                                                                    \
@@ -466,10 +419,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   {                                                                                      \
     float p0 = 0.f, p1 = 0.f;                                                            \
     _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float d0 = __uint_as_float(V[j4 * 4 + 0]);                                   \
-      const float d1 = __uint_as_float(V[j4 * 4 + 1]);                                   \
-      const float d2 = __uint_as_float(V[j4 * 4 + 2]);                                   \
-      const float d3 = __uint_as_float(V[j4 * 4 + 3]);                                   \
+      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
+      const float d0 = __uint_as_float(V[j4 * 4 + 0]) + cn4.x;                           \
+      const float d1 = __uint_as_float(V[j4 * 4 + 1]) + cn4.y;                           \
+      const float d2 = __uint_as_float(V[j4 * 4 + 2]) + cn4.z;                           \
+      const float d3 = __uint_as_float(V[j4 * 4 + 3]) + cn4.w;                           \
       p0 = fmaf(d0 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 0) * 0.0009765625f, p0);   \
       p1 = fmaf(d1 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 1) * 0.0009765625f, p1);   \
       p0 = fmaf(d2 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 2) * 0.0009765625f, p0);   \
@@ -521,126 +475,96 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     }
   } else if (warp >= 12) {
     // =========================== distance + M-step warps ===========================
-    // Cluster c is owned by warp c % 8, lane c / 8, which keeps the d (<= 64) running sums of that
-    // cluster in 64 registers.  Per 32-row quarter tile the rows are routed to their owner lanes through a
-    // small shared-memory list (rank among equal owners from __match_any_sync, no atomics); then every
-    // owner lane adds ITS row with statically indexed registers - up to 32 rows are accumulated
-    // concurrently and there is no per-row branch tree.  When distances are requested the same lane
-    // re-evaluates the winning distance exactly in direct form sum (x-c)^2, c = -(bhi+blo)/2.
+    // Warp wm owns the rows whose label c satisfies c % 8 == wm.  Lane l holds features l and l+32 of
+    // the row (conflict-free reads of the swizzled tile): (a) the winning distance is re-evaluated
+    // exactly in fp32 direct form sum (x-c)^2 with c = -(bhi+blo)/2 read from the resident B tiles,
+    // (b) [MSTEP] the row is added to the register-resident sums of cluster c.
     const int wm = warp - 12;
-    float acc[64];
+    float acc[32][2];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 32; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
     int cnt = 0;
     double inertia_acc = 0.0;
     const bool two = KB > 1;
-    const int myc = wm + 8 * lane;                       // the cluster this lane owns
-    const uint32_t csw = (uint32_t)(myc & 7);
-    unsigned char* lst = smem + cfg.off_list + wm * 128;  // [32 owner lanes][4 row slots]
     mbar_wait(BAR(BAR_B_FULL), 0);
-#define MSTEP_PROCESS(RH, ROWG)                                                                       \
-  {                                                                                                   \
-    const unsigned char* xr = xs + (RH) * 128;                                                        \
-    const uint32_t rsw = (uint32_t)((RH) & 7);                                                        \
-    float s2 = 0.f;                                                                                   \
-    _Pragma("unroll") for (int kb = 0; kb < 2; ++kb) {                                                \
-      if (kb == 0 || two) {                                                                           \
-        _Pragma("unroll") for (int q = 0; q < 8; ++q) {                                               \
-          const float4 v = *reinterpret_cast<const float4*>(xr + kb * MKBLK_BYTES + ((q ^ rsw) << 4)); \
-          if (MSTEP) {                                                                                \
-            acc[kb * 32 + q * 4 + 0] += v.x; acc[kb * 32 + q * 4 + 1] += v.y;                         \
-            acc[kb * 32 + q * 4 + 2] += v.z; acc[kb * 32 + q * 4 + 3] += v.w;                         \
-          }                                                                                           \
-          if (WANT_DIST) {                                                                            \
-            const uint32_t bo = (uint32_t)kb * NP * 128u + (uint32_t)myc * 128u + ((q ^ csw) << 4);  \
-            const float4 h4 = *reinterpret_cast<const float4*>(smem + cfg.off_bhi + bo);              \
-            const float4 l4 = *reinterpret_cast<const float4*>(smem + cfg.off_blo + bo);              \
-            float t;                                                                                  \
-            t = fmaf(0.5f, h4.x + l4.x, v.x); s2 = fmaf(t, t, s2);                                    \
-            t = fmaf(0.5f, h4.y + l4.y, v.y); s2 = fmaf(t, t, s2);                                    \
-            t = fmaf(0.5f, h4.z + l4.z, v.z); s2 = fmaf(t, t, s2);                                    \
-            t = fmaf(0.5f, h4.w + l4.w, v.w); s2 = fmaf(t, t, s2);                                    \
-          }                                                                                           \
-        }                                                                                             \
-      }                                                                                               \
-    }                                                                                                 \
-    cnt += 1;                                                                                         \
-    if (WANT_DIST) {                                                                                  \
-      const float outv = a.squared ? s2 : sqrtf(s2);                                                  \
-      inertia_acc += (double)outv;                                                                    \
-      if (a.min_out) reinterpret_cast<float*>(a.min_out)[(ROWG)] = outv;                              \
-    }                                                                                                 \
-  }
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
+      const int stage = (int)(it % NST);
       const int lb = (int)(it & 1);
+      if (wm == 0) {
+        mbar_wait_sleep(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+        mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+      }
+      named_bar_sync(1, 256);            // the other 7 warps park here (no polling, no issue slots)
+      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
 #pragma unroll 1
-      for (int h = 0; h < 4; ++h) {
-        const long long mi = it * 4 + h;
-        const int slot = (int)(mi % MST);
-        // every warp polls on its own (no cross-warp barrier: the warps of a quarter need not stay in step)
-        if (h == 0) mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
-        mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((mi / MST) & 1));
-        const unsigned char* xs = smem + cfg.off_m + slot * (KB * MKBLK_BYTES);
-        *reinterpret_cast<uint32_t*>(lst + lane * 4) = 0xFFFFFFFFu;
-        const int ml = lab_s[lb * BM + h * MH + lane];
-        const bool mine = ml >= 0 && (ml & 7) == wm;
-        const int owner = (ml >> 3) & 31;
-        __syncwarp();
-        // slot claim: unassigned rows write their id into slot t of their owner, the value that sticks wins
-        bool todo = mine;
+      for (int base = 0; base < BM; base += 32) {
+        const int ml = lab_s[lb * BM + base + lane];
+        unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
+#pragma unroll 1
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int c = __shfl_sync(0xffffffffu, ml, b) & 255;
+          const int row = base + b;
+          const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
+          const float x0 = *reinterpret_cast<const float*>(xs + ro);
+          const float x1 = two ? *reinterpret_cast<const float*>(xs + KBLK_BYTES + ro) : 0.f;
+          if (WANT_DIST) {
+            const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2));
+            float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +
+                                 *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);
+            float s2 = t * t;
+            if (two) {
+              const uint32_t c1 = co + (uint32_t)NP * 128u;
+              t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +
+                             *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);
+              s2 = fmaf(t, t, s2);
+            }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (__any_sync(0xffffffffu, todo)) {
-            if (todo) lst[owner * 4 + t] = (unsigned char)lane;
-            __syncwarp();
-            if (todo && lst[owner * 4 + t] == (unsigned char)lane) todo = false;
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) {
+              const float outv = a.squared ? s2 : sqrtf(s2);
+              inertia_acc += (double)outv;
+              if (a.min_out) reinterpret_cast<float*>(a.min_out)[tile * BM + row] = outv;
+            }
           }
-        }
-        unsigned ovf = __ballot_sync(0xffffffffu, todo);
-        __syncwarp();
-        const uint32_t e = *reinterpret_cast<const uint32_t*>(lst + lane * 4);
-        const long long rowg0 = tile * BM + h * MH;
-        // one loop (a single instantiation of the 64-register update) walks the list slots - ranks are
-        // dense, so an empty slot ends them - and then the rare overflow rows
-        int rr = 0;
-#pragma unroll 1
-        while (true) {
-          int rh;
-          bool v;
-          if (rr < 4) {
-            rh = (int)((e >> (8 * rr)) & 0xFFu);
-            v = rh != 0xFF;
-            ++rr;
-            if (!__any_sync(0xffffffffu, v)) { rr = 4; continue; }
-          } else if (ovf) {            // more than 4 rows of one cluster in this quarter: rare, serial
-            rh = __ffs(ovf) - 1;
-            ovf &= ovf - 1;
-            v = lane == ((__shfl_sync(0xffffffffu, ml, rh) >> 3) & 31);
-          } else {
-            break;
+          if (MSTEP) {
+            const int cl = c >> 3;
+            switch (cl) {
+              ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)
+              ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)
+              ACC32_CASE(12) ACC32_CASE(13) ACC32_CASE(14) ACC32_CASE(15) ACC32_CASE(16) ACC32_CASE(17)
+              ACC32_CASE(18) ACC32_CASE(19) ACC32_CASE(20) ACC32_CASE(21) ACC32_CASE(22) ACC32_CASE(23)
+              ACC32_CASE(24) ACC32_CASE(25) ACC32_CASE(26) ACC32_CASE(27) ACC32_CASE(28) ACC32_CASE(29)
+              ACC32_CASE(30) ACC32_CASE(31)
+              default: break;
+            }
+            cnt += (lane == cl) ? 1 : 0;
           }
-          if (v) MSTEP_PROCESS(rh, rowg0 + rh)
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(BAR(BAR_M_EMPTY + slot));
-          if (h == 3) mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
         }
       }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+        mbar_arrive(BAR(BAR_X_EMPTY + stage));
+      }
     }
-#undef MSTEP_PROCESS
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, o);
     if (lane == 0) red_s[wm] = inertia_acc;
-    if (MSTEP && myc < a.k) {
-      // flush this lane's cluster sums (one 4*d byte row) and count
-      float* g = reinterpret_cast<float*>(a.psum) + ((size_t)blockIdx.x * a.k + myc) * a.d;
+    if (MSTEP) {
+      // flush the register-resident sums: cluster c = wm + 8 j, features lane and lane + 32
+      float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d;
 #pragma unroll
-      for (int f = 0; f < 64; ++f)
-        if (f < a.d) g[f] = acc[f];
-      a.pcnt[(size_t)blockIdx.x * a.k + myc] = cnt;
+      for (int j = 0; j < 32; ++j) {
+        const int c = wm + 8 * j;
+        if (c < a.k) {
+          if (lane < a.d) g[(size_t)c * a.d + lane] = acc[j][0];
+          if (lane + 32 < a.d) g[(size_t)c * a.d + lane + 32] = acc[j][1];
+        }
+      }
+      const int cc = wm + 8 * lane;
+      if (cc < a.k) a.pcnt[(size_t)blockIdx.x * a.k + cc] = cnt;
     }
   }
 
@@ -784,12 +708,8 @@ static bool make_cfg(int d, int k, TcCfg* c) {
     c->off_bhi = o; o += bbytes;
     c->off_blo = o; o += bbytes;
     o = (uint32_t)align_up(o, 1024);
-    c->off_bcn = o; o += (uint32_t)c->NP * 32u;                  // ||c||^2 operand tile
-    o = (uint32_t)align_up(o, 1024);
-    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring (MMA + Xlo converter)
-    c->off_m = o; o += (uint32_t)MST * c->KB * MKBLK_BYTES;      // M ring (M-step / distance warps)
-    c->off_cn = o;
-    c->off_list = o; o += 8 * 128;                               // M-step row routing lists
+    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;
+    c->off_cn = o; o += (uint32_t)c->NP * 4;
     c->off_lab = o; o += 2 * BM * 4;
     c->off_flist = o;
     c->off_red = o; o += 72;
@@ -806,10 +726,8 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
   TcCfg cfg;
   if (!make_cfg(a.d, a.k, &cfg)) return BKM_EUNSUPPORTED;
-  CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
+  CUtensorMap tm_x, tm_bhi, tm_blo;
   int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
-  if (rc) return rc;
-  rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, MH);
   if (rc) return rc;
   rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
   if (rc) return rc;
@@ -825,7 +743,7 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   {                                                                                                           \
     BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                       (int)cfg.total));                                                       \
-    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);                  \
+    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);                  \
   }
   if (mstep) { if (want_dist) TC_LAUNCH(true, true) else TC_LAUNCH(true, false) }
   else TC_LAUNCH(false, true)
