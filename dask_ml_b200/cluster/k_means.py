@@ -173,9 +173,18 @@ class KMeans(TransformerMixin, BaseEstimator):
         self.n_features_in_ = centroids.shape[1]
         return self
 
+    def _check_n_features(self, X):
+        d = X.d if isinstance(X, DeviceData) else X.shape[1]
+        n_in = getattr(self, "n_features_in_", self.cluster_centers_.shape[1])
+        if d != n_in:
+            raise ValueError(
+                "X has {} features, but {} is expecting {} features as input.".format(d, type(self).__name__, n_in)
+            )
+
     def transform(self, X, y=None):
         check_is_fitted(self, "cluster_centers_")
         X = self._check_array(X)
+        self._check_n_features(X)
         from ..metrics.pairwise import euclidean_distances
 
         return euclidean_distances(X, self.cluster_centers_)
@@ -184,6 +193,7 @@ class KMeans(TransformerMixin, BaseEstimator):
         """Index of the closest centre for every row (k_means.py:212-233); int32 labels."""
         check_is_fitted(self, "cluster_centers_")
         X = self._check_array(X)
+        self._check_n_features(X)
         from ..metrics.pairwise import pairwise_distances_argmin_min
 
         labels = pairwise_distances_argmin_min(X, self.cluster_centers_)[0].astype(np.int32)

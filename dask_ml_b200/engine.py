@@ -115,7 +115,10 @@ class CudaBackend(object):
         if _is_torch(block):
             t = block
         else:
-            t = torch.from_numpy(np.ascontiguousarray(block))
+            a = np.ascontiguousarray(block)
+            if not a.flags.writeable:
+                a = a.copy()                 # torch refuses read-only buffers
+            t = torch.from_numpy(a)
         t = t.to(device=self.device, dtype=dtype, non_blocking=True)
         return t.contiguous()
 

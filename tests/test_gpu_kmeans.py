@@ -205,3 +205,18 @@ def test_kmeans_parallel_init_quality(oracle):
     # inertia_ follows the reference's Q4 rule; compare through predict on the fitted centres
     d = ((X[:, None, :].astype(np.float64) - a.cluster_centers_[None].astype(np.float64)) ** 2).sum(-1).min(1).sum()
     assert d <= 1.05 * b.inertia_
+
+
+def test_check_estimator():
+    """reference tests/test_kmeans.py:21-24 — scikit-learn API conformance."""
+    import warnings
+
+    from sklearn.utils.estimator_checks import check_estimator
+
+    from dask_ml_b200.cluster import KMeans
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = check_estimator(KMeans(), on_fail=None)
+    bad = [(r["check_name"], str(r["exception"])[:200]) for r in res if r["status"] == "failed"]
+    assert not bad, bad

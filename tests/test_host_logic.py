@@ -129,6 +129,8 @@ def test_predict_transform_and_dtypes(cpu_engine):
         assert a.transform(yy).dtype == b.transform(yy).dtype
         p = a.predict(xx)
         assert p.dtype == np.int32 and p.shape == (100,)
+        with pytest.raises(ValueError, match="features"):
+            a.predict(np.zeros((5, 3)))
         d = ((xx[:, None, :].astype(float) - a.cluster_centers_[None].astype(float)) ** 2).sum(-1)
         np.testing.assert_array_equal(p.compute(), d.argmin(1))
 
