@@ -30,8 +30,11 @@
 namespace bkm {
 
 static const int BM = 128;           // rows per tile
-static const int TC_THREADS = 640;
+static const int NMW = 16;               // distance + M-step warps (each owns the clusters c % NMW == its index)
+static const int TC_THREADS = (12 + NMW) * 32;
 static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
+static const int MH = 32;                 // rows per M-ring stage (a quarter tile)
+static const int MKBLK_BYTES = MH * 128;
 
 struct TcCfg {
   int KB;        // 32-float K-blocks per row (1 or 2)
@@ -40,24 +43,36 @@ struct TcCfg {
   int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
   int U;
   int NST;       // X stages
-  uint32_t off_bhi, off_blo, off_x, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
+  uint32_t off_bhi, off_blo, off_bcn, off_ones, off_x, off_m, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
 };
+
+static const int NBUF = 3;               // 128-column TMEM accumulator buffers (3*128 + 2*64 Xlo = 512 columns)
 
 enum {
   BAR_B_FULL = 0,
   BAR_X_FULL = 1,       // [NST<=4]
   BAR_X_EMPTY = 5,      // [4]
-  BAR_ACC_FULL = 9,     // [set 2][buf 2]  one barrier per (epilogue warp set, accumulator buffer): every
-  BAR_ACC_EMPTY = 13,   // [set 2][buf 2]  waiter then observes consecutive phases (no parity aliasing)
-  BAR_XLO_FULL = 17,    // [2]
-  BAR_LAB_FULL = 19,    // [2]
-  BAR_LAB_EMPTY = 21,   // [2]
-  BAR_COUNT = 23
+  BAR_ACC_FULL = 9,     // [set 2][buf 3]  one barrier per (epilogue warp set, accumulator buffer): every
+  BAR_ACC_EMPTY = 15,   // [set 2][buf 3]  waiter then observes consecutive phases (no parity aliasing)
+  BAR_XLO_FULL = 21,    // [2]
+  BAR_LAB_FULL = 23,    // [2]
+  BAR_LAB_EMPTY = 25,   // [2]
+  BAR_M_FULL = 27,      // [2]  M ring: 64-row half tiles re-fetched (L2 hits) for the M-step warps
+  BAR_M_EMPTY = 29,     // [2]
+  BAR_COUNT = 31
 };
 
 // ------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Accumulator unit g (g = tile*U + u) uses TMEM buffer g % NBUF and is consumed by epilogue set (g/U) & 1.
+// Parity of the phase of barrier [set][buf] that belongs to unit g = number of earlier units with the same
+// (set, buffer), mod 2.  The pattern repeats every lcm(2U, 3) units: U=1 -> each pair once per 6 units,
+// U=2 -> twice per 12 units (second occurrences: g % 12 in {4,6,8,9,10,11}).
+__device__ __forceinline__ uint32_t acc_parity(long long g, int U) {
+  if (U == 1) return (uint32_t)((g / 6) & 1);
+  return (uint32_t)((0xF50u >> (int)(g % 12)) & 1u);
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -111,6 +126,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
   float d;
@@ -179,13 +197,13 @@ __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r
 template <bool MSTEP, bool WANT_DIST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
+                const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                const __grid_constant__ CUtensorMap tm_xm) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
   if (tid == 0 && (sbase & 1023)) __trap();
   const uint32_t s_bhi = sbase + cfg.off_bhi, s_blo = sbase + cfg.off_blo, s_x = sbase + cfg.off_x;
-  float* cn_s = reinterpret_cast<float*>(smem + cfg.off_cn);
   int* lab_s = reinterpret_cast<int*>(smem + cfg.off_lab);          // [2][BM]
   double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [5]
   const uint32_t bars = sbase + cfg.off_bar;
@@ -202,21 +220,24 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xm));
     mbar_init(BAR(BAR_B_FULL), 1);
     for (int s = 0; s < 4; ++s) {
       mbar_init(BAR(BAR_X_FULL + s), 1);
-      mbar_init(BAR(BAR_X_EMPTY + s), 8);
+      mbar_init(BAR(BAR_X_EMPTY + s), 1);
     }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 2 * NBUF; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
       mbar_init(BAR(BAR_ACC_EMPTY + b), 128);
     }
     for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR(BAR_M_FULL + b), 1);
+      mbar_init(BAR(BAR_M_EMPTY + b), NMW);
       mbar_init(BAR(BAR_XLO_FULL + b), 128);
       mbar_init(BAR(BAR_LAB_FULL + b), 128);
-      mbar_init(BAR(BAR_LAB_EMPTY + b), 8);
+      mbar_init(BAR(BAR_LAB_EMPTY + b), NMW);
     }
-    red_s[8] = 0.0;
+    red_s[NMW] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -224,8 +245,16 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   {
-    const float* gcn = reinterpret_cast<const float*>(a.pack + a.L.off_cn32);
-    for (int i = tid; i < NP; i += TC_THREADS) cn_s[i] = gcn[i];
+    // ||c||^2 enters the accumulator through one extra MMA K-step: B rows [hi,mid,lo,0,...] (exact 3-way
+    // tf32 split, built by pack_norms_kernel) against a constant A tile of rows [1,1,1,0,...]; both tiles
+    // use the canonical no-swizzle K-major layout (8-row groups of 256 B).  Plain stores + proxy fence.
+    const float4* g = reinterpret_cast<const float4*>(a.pack + a.L.off_bcn);
+    float4* sdst = reinterpret_cast<float4*>(smem + cfg.off_bcn);
+    for (int i = tid; i < NP * 2; i += TC_THREADS) sdst[i] = g[i];
+    float4* odst = reinterpret_cast<float4*>(smem + cfg.off_ones);
+    for (int i = tid; i < BM * 2; i += TC_THREADS)
+      odst[i] = ((i >> 3) & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(1.f, 1.f, 1.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -240,16 +269,40 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         tma_load_2d(s_bhi + (uint32_t)kb * NP * 128u, &tm_bhi, BAR(BAR_B_FULL), kb * 32, 0);
         tma_load_2d(s_blo + (uint32_t)kb * NP * 128u, &tm_blo, BAR(BAR_B_FULL), kb * 32, 0);
       }
+      const int PF = 6;        // L2 prefetch distance (tiles) ahead of the shared-memory ring
+      for (long long it = 0; it < PF && it < my_tiles; ++it)
+        for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((blockIdx.x + it * gridDim.x) * BM));
 #pragma unroll 1
       for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * gridDim.x;
         const int stage = (int)(it % NST);
         const uint32_t ph = (uint32_t)((it / NST) & 1);
-        mbar_wait_sleep(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
+        if (it + PF < my_tiles)
+          for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((tile + (long long)PF * gridDim.x) * BM));
+        mbar_wait(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
         mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
                       kb * 32, (int)(tile * BM));
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== TMA producer of the M ring ===========================
+    // Re-fetches every tile as two 64-row halves for the M-step / distance warps.  The same rows were
+    // loaded for the MMA a few microseconds earlier, so these are L2 hits: HBM traffic stays at one read
+    // of X per iteration while the M-step no longer holds the MMA's shared-memory stages.
+    if (lane == 0) {
+      const uint32_t s_m = sbase + cfg.off_m;
+      const uint32_t mbytes = (uint32_t)KB * MKBLK_BYTES;
+#pragma unroll 1
+      for (long long mi = 0; mi < 4 * my_tiles; ++mi) {
+        const long long tile = blockIdx.x + (mi >> 2) * gridDim.x;
+        const int slot = (int)(mi & 1);
+        mbar_wait(BAR(BAR_M_EMPTY + slot), (uint32_t)(((mi >> 1) & 1) ^ 1));
+        mbar_expect_tx(BAR(BAR_M_FULL + slot), mbytes);
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_2d(s_m + slot * mbytes + (uint32_t)kb * MKBLK_BYTES, &tm_xm, BAR(BAR_M_FULL + slot), kb * 32,
+                      (int)(tile * BM + (mi & 3) * MH));
       }
     }
   } else if (warp == 1) {
@@ -261,23 +314,26 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     tc_fence_after();
     const uint64_t dflags = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     const uint32_t bblk = (uint32_t)NP * 128u;          // bytes of one K-block of a B tile
+    // no-swizzle K-major operands of the ||c||^2 K-step: LBO = 128 B (second 16-byte K chunk), SBO = 256 B
+    const uint64_t dns = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint64_t dcn = dns | (uint64_t)(((sbase + cfg.off_bcn) >> 4) & 0x3FFF);
+    const uint64_t dones = dns | (uint64_t)(((sbase + cfg.off_ones) >> 4) & 0x3FFF);
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const int stage = (int)(it % NST);
       const uint32_t ph = (uint32_t)((it / NST) & 1);
       const uint32_t xs = s_x + stage * stage_bytes;
-      const uint32_t xlo_t = tmem + 256u + (uint32_t)(it & 1) * 64u;
+      const uint32_t xlo_t = tmem + 384u + (uint32_t)(it & 1) * 64u;
       mbar_wait(BAR(BAR_X_FULL + stage), ph);
       tc_fence_after();
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const long long g = it * U + u;
-        const int buf = (int)(g & 1);
-        if (g >= 2) {
-          // buffer `buf` was last used by unit g-2: tile pt, consumed by epilogue set pt&1 as that set's
-          // (pt>>1)-th tile
-          const long long pt = (g - 2) / U;
-          mbar_wait(BAR(BAR_ACC_EMPTY + (int)(pt & 1) * 2 + buf), (uint32_t)((pt >> 1) & 1));
+        const int buf = (int)(g % NBUF);
+        if (g >= NBUF) {
+          // the buffer was last used by unit g-NBUF, consumed by epilogue set ((g-NBUF)/U) & 1
+          const long long gp = g - NBUF;
+          mbar_wait(BAR(BAR_ACC_EMPTY + (int)((gp / U) & 1) * NBUF + buf), acc_parity(gp, U));
         }
         tc_fence_after();
         const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
@@ -320,7 +376,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
               mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + bo, idesc, 1u);
             }
           }
-          tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * 2 + buf));
+          mma_tf32_ss(d_t, dones, dcn + (uint64_t)(rowoff >> 6), idesc, 1u);     // + ||c_j||^2
+          tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * NBUF + buf));
+          // the smem stage is free once every MMA of this tile has read it (the Xlo converter finished
+          // before pass 3 could start); later consumers (M-step) read their rows from L2 instead
+          if (u == U - 1) tc_commit(BAR(BAR_X_EMPTY + stage));
         }
         __syncwarp();
       }
@@ -362,7 +422,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
               v[q * 4 + i] = __float_as_uint(e[i] - hi);     // exact: the 13 low mantissa bits
             }
           }
-          TC_ST32(tmem + lane_addr + 256u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u, v);
+          TC_ST32(tmem + lane_addr + 384u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u, v);
         }
         xn = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -379,10 +439,10 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const long long g = it * U + u;
-        const int buf = (int)(g & 1);
+        const int buf = (int)(g % NBUF);
         const int nch = (u == 0 ? cfg.NU0 : cfg.NU1) >> 4;
         const int col0 = u == 0 ? 0 : cfg.NU0;
-        mbar_wait(BAR(BAR_ACC_FULL + set * 2 + buf), (uint32_t)((it >> 1) & 1));   // this set's (it>>1)-th tile
+        mbar_wait(BAR(BAR_ACC_FULL + set * NBUF + buf), acc_parity(g, U));
         tc_fence_after();
         const uint32_t tbase = tmem + lane_addr + (uint32_t)buf * 128u;
         uint32_t v0[16], v1[16];
@@ -390,11 +450,10 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #define EPI_MIN(V, COLBASE)                                                              \
   {                                                                                      \
     _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
-      const float d0 = __uint_as_float(V[j4 * 4 + 0]) + cn4.x;                           \
-      const float d1 = __uint_as_float(V[j4 * 4 + 1]) + cn4.y;                           \
-      const float d2 = __uint_as_float(V[j4 * 4 + 2]) + cn4.z;                           \
-      const float d3 = __uint_as_float(V[j4 * 4 + 3]) + cn4.w;                           \
+      const float d0 = __uint_as_float(V[j4 * 4 + 0]);                                   \
+      const float d1 = __uint_as_float(V[j4 * 4 + 1]);                                   \
+      const float d2 = __uint_as_float(V[j4 * 4 + 2]);                                   \
+      const float d3 = __uint_as_float(V[j4 * 4 + 3]);                                   \
       ma = fmin3(ma, d0, d1);                                                            \
       mb = fmin3(mb, d2, d3);                                                            \
     }                                                                                    \
@@ -419,11 +478,10 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   {                                                                                      \
     float p0 = 0.f, p1 = 0.f;                                                            \
     _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float4 cn4 = *reinterpret_cast<const float4*>(cn_s + (COLBASE) + j4 * 4);   \
-      const float d0 = __uint_as_float(V[j4 * 4 + 0]) + cn4.x;                           \
-      const float d1 = __uint_as_float(V[j4 * 4 + 1]) + cn4.y;                           \
-      const float d2 = __uint_as_float(V[j4 * 4 + 2]) + cn4.z;                           \
-      const float d3 = __uint_as_float(V[j4 * 4 + 3]) + cn4.w;                           \
+      const float d0 = __uint_as_float(V[j4 * 4 + 0]);                                   \
+      const float d1 = __uint_as_float(V[j4 * 4 + 1]);                                   \
+      const float d2 = __uint_as_float(V[j4 * 4 + 2]);                                   \
+      const float d3 = __uint_as_float(V[j4 * 4 + 3]);                                   \
       p0 = fmaf(d0 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 0) * 0.0009765625f, p0);   \
       p1 = fmaf(d1 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 1) * 0.0009765625f, p1);   \
       p0 = fmaf(d2 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 2) * 0.0009765625f, p0);   \
@@ -447,7 +505,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         }
 #undef EPI_HIT
         tc_fence_before();
-        mbar_arrive(BAR(BAR_ACC_EMPTY + set * 2 + buf));
+        mbar_arrive(BAR(BAR_ACC_EMPTY + set * NBUF + buf));
         // acc < 2: one hit, (acc - 1) * 1024 = index inside its 16-column chunk, accb = that chunk's base
         const float dec = acc < 2.f ? accb + (acc - 1.f) * 1024.f : -1.f;
         if (u == 0) { um0 = m; ua0 = dec; } else { um1 = m; ua1 = dec; }
@@ -480,91 +538,98 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     // exactly in fp32 direct form sum (x-c)^2 with c = -(bhi+blo)/2 read from the resident B tiles,
     // (b) [MSTEP] the row is added to the register-resident sums of cluster c.
     const int wm = warp - 12;
-    float acc[32][2];
+    float acc[256 / NMW][2];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+    for (int j = 0; j < 256 / NMW; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
     int cnt = 0;
     double inertia_acc = 0.0;
     const bool two = KB > 1;
     mbar_wait(BAR(BAR_B_FULL), 0);
+#define MSTEP_ROW(XA, XB, CC, ROWG)                                                               \
+  {                                                                                               \
+    const int c = (CC);                                                                           \
+    const float x0 = (XA), x1 = (XB);                                                             \
+    if (WANT_DIST) {                                                                              \
+      const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2)); \
+      float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +             \
+                           *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);         \
+      float s2 = t * t;                                                                           \
+      if (two) {                                                                                  \
+        const uint32_t c1 = co + (uint32_t)NP * 128u;                                             \
+        t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +                 \
+                       *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);             \
+        s2 = fmaf(t, t, s2);                                                                      \
+      }                                                                                           \
+      _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o); \
+      if (lane == 0) {                                                                            \
+        const float outv = a.squared ? s2 : sqrtf(s2);                                            \
+        inertia_acc += (double)outv;                                                              \
+        if (a.min_out) reinterpret_cast<float*>(a.min_out)[(ROWG)] = outv;                        \
+      }                                                                                           \
+    }                                                                                             \
+    if (MSTEP) {                                                                                  \
+      const int cl = c / NMW;                                                                     \
+      switch (cl) {                                                                               \
+        ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)       \
+        ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)     \
+        ACC32_CASE(12) ACC32_CASE(13) ACC32_CASE(14) ACC32_CASE(15)                               \
+        default: break;                                                                           \
+      }                                                                                           \
+      cnt += (lane == cl) ? 1 : 0;                                                                \
+    }                                                                                             \
+  }
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const int stage = (int)(it % NST);
       const int lb = (int)(it & 1);
-      if (wm == 0) {
-        mbar_wait_sleep(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
-        mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
-      }
-      named_bar_sync(1, 256);            // the other 7 warps park here (no polling, no issue slots)
-      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
 #pragma unroll 1
-      for (int base = 0; base < BM; base += 32) {
-        const int ml = lab_s[lb * BM + base + lane];
-        unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & 7) == wm);
+      for (int h = 0; h < 4; ++h) {
+        const long long mi = it * 4 + h;
+        const int slot = (int)(mi & 1);
+        if (wm == 0) {
+          if (h == 0) mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+          mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((mi >> 1) & 1));
+        }
+        named_bar_sync(1, NMW * 32);          // the other 7 warps park here (no polling, no issue slots)
+        const unsigned char* xs = smem + cfg.off_m + slot * (KB * MKBLK_BYTES);
 #pragma unroll 1
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const int c = __shfl_sync(0xffffffffu, ml, b) & 255;
-          const int row = base + b;
-          const uint32_t ro = (uint32_t)(row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + ((lane & 3) << 2));
-          const float x0 = *reinterpret_cast<const float*>(xs + ro);
-          const float x1 = two ? *reinterpret_cast<const float*>(xs + KBLK_BYTES + ro) : 0.f;
-          if (WANT_DIST) {
-            const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2));
-            float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +
-                                 *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);
-            float s2 = t * t;
-            if (two) {
-              const uint32_t c1 = co + (uint32_t)NP * 128u;
-              t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +
-                             *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);
-              s2 = fmaf(t, t, s2);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            if (lane == 0) {
-              const float outv = a.squared ? s2 : sqrtf(s2);
-              inertia_acc += (double)outv;
-              if (a.min_out) reinterpret_cast<float*>(a.min_out)[tile * BM + row] = outv;
-            }
-          }
-          if (MSTEP) {
-            const int cl = c >> 3;
-            switch (cl) {
-              ACC32_CASE(0) ACC32_CASE(1) ACC32_CASE(2) ACC32_CASE(3) ACC32_CASE(4) ACC32_CASE(5)
-              ACC32_CASE(6) ACC32_CASE(7) ACC32_CASE(8) ACC32_CASE(9) ACC32_CASE(10) ACC32_CASE(11)
-              ACC32_CASE(12) ACC32_CASE(13) ACC32_CASE(14) ACC32_CASE(15) ACC32_CASE(16) ACC32_CASE(17)
-              ACC32_CASE(18) ACC32_CASE(19) ACC32_CASE(20) ACC32_CASE(21) ACC32_CASE(22) ACC32_CASE(23)
-              ACC32_CASE(24) ACC32_CASE(25) ACC32_CASE(26) ACC32_CASE(27) ACC32_CASE(28) ACC32_CASE(29)
-              ACC32_CASE(30) ACC32_CASE(31)
-              default: break;
-            }
-            cnt += (lane == cl) ? 1 : 0;
+        for (int base = 0; base < MH; base += 32) {
+          const int ml = lab_s[lb * BM + h * MH + base + lane];
+          unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & (NMW - 1)) == wm);
+#pragma unroll 1
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int cq = __shfl_sync(0xffffffffu, ml, b) & 255;
+            const int rh = base + b;      // row inside the 64-row half tile
+            const uint32_t ro = (uint32_t)(rh * 128 + (((lane >> 2) ^ (rh & 7)) << 4) + ((lane & 3) << 2));
+            const float xa = *reinterpret_cast<const float*>(xs + ro);
+            const float xb = two ? *reinterpret_cast<const float*>(xs + MKBLK_BYTES + ro) : 0.f;
+            MSTEP_ROW(xa, xb, cq, tile * BM + h * MH + base + b)
           }
         }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
-        mbar_arrive(BAR(BAR_X_EMPTY + stage));
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(BAR(BAR_M_EMPTY + slot));
+          if (h == 3) mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+        }
       }
     }
+#undef MSTEP_ROW
     if (lane == 0) red_s[wm] = inertia_acc;
     if (MSTEP) {
       // flush the register-resident sums: cluster c = wm + 8 j, features lane and lane + 32
       float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = wm + 8 * j;
+      for (int j = 0; j < 256 / NMW; ++j) {
+        const int c = wm + NMW * j;
         if (c < a.k) {
           if (lane < a.d) g[(size_t)c * a.d + lane] = acc[j][0];
           if (lane + 32 < a.d) g[(size_t)c * a.d + lane + 32] = acc[j][1];
         }
       }
-      const int cc = wm + 8 * lane;
-      if (cc < a.k) a.pcnt[(size_t)blockIdx.x * a.k + cc] = cnt;
+      const int cc = wm + NMW * lane;
+      if (lane < 256 / NMW && cc < a.k) a.pcnt[(size_t)blockIdx.x * a.k + cc] = cnt;
     }
   }
 
@@ -573,8 +638,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    double t = red_s[8];
-    for (int w = 0; w < 8; ++w) t += red_s[w];
+    double t = red_s[NMW];
+    for (int w = 0; w < NMW; ++w) t += red_s[w];
     a.pin[blockIdx.x] = t;
   }
   if (warp == 2) {
@@ -708,11 +773,15 @@ static bool make_cfg(int d, int k, TcCfg* c) {
     c->off_bhi = o; o += bbytes;
     c->off_blo = o; o += bbytes;
     o = (uint32_t)align_up(o, 1024);
-    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;
-    c->off_cn = o; o += (uint32_t)c->NP * 4;
+    c->off_bcn = o; o += (uint32_t)c->NP * 32u;                  // ||c||^2 operand tile
+    c->off_ones = o; o += BM * 32u;                              // constant [1,1,1,0..] A tile
+    o = (uint32_t)align_up(o, 1024);
+    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring (MMA + Xlo converter)
+    c->off_m = o; o += 2u * c->KB * MKBLK_BYTES;                 // M ring (M-step / distance warps)
+    c->off_cn = o;
     c->off_lab = o; o += 2 * BM * 4;
     c->off_flist = o;
-    c->off_red = o; o += 72;
+    c->off_red = o; o += (NMW + 1) * 8;
     c->off_bar = o; o += BAR_COUNT * 8;
     c->off_tptr = o; o += 16;
     c->total = o;
@@ -726,8 +795,10 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
   TcCfg cfg;
   if (!make_cfg(a.d, a.k, &cfg)) return BKM_EUNSUPPORTED;
-  CUtensorMap tm_x, tm_bhi, tm_blo;
+  CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
   int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
+  if (rc) return rc;
+  rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, MH);
   if (rc) return rc;
   rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
   if (rc) return rc;
@@ -743,7 +814,7 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   {                                                                                                           \
     BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                       (int)cfg.total));                                                       \
-    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo);                  \
+    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);                  \
   }
   if (mstep) { if (want_dist) TC_LAUNCH(true, true) else TC_LAUNCH(true, false) }
   else TC_LAUNCH(false, true)
