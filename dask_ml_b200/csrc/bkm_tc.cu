@@ -586,11 +586,10 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       for (int h = 0; h < 4; ++h) {
         const long long mi = it * 4 + h;
         const int slot = (int)(mi & 1);
-        if (wm == 0) {
-          if (h == 0) mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
-          mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((mi >> 1) & 1));
-        }
-        named_bar_sync(1, NMW * 32);          // the other 7 warps park here (no polling, no issue slots)
+        // every warp polls on its own: a per-quarter barrier across the 16 warps would make each quarter
+        // as slow as its most loaded warp
+        if (h == 0) mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
+        mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((mi >> 1) & 1));
         const unsigned char* xs = smem + cfg.off_m + slot * (KB * MKBLK_BYTES);
 #pragma unroll 1
         for (int base = 0; base < MH; base += 32) {
