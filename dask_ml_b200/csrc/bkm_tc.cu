@@ -92,10 +92,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > (1u << 22) || ((spin & 1023) == 1023 && *(volatile unsigned int*)&g_tc_abort)) {
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // suspend-time hint: the hardware
+        "selp.u32 %0, 1, 0, p;\n}"                                        // parks the warp instead of polling
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+    if (spin > (1u << 18) || ((spin & 1023) == 1023 && *(volatile unsigned int*)&g_tc_abort)) {
       atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
       if (spin > 2048 && (threadIdx.x & 31) == 0) g_tc_dbg[threadIdx.x >> 5] = 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | blockIdx.x;
       return;
