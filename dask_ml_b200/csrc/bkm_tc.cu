@@ -2,27 +2,23 @@
 //
 // Shapes: fp32 X with d % 4 == 0, d <= 64, k <= 256 (BASELINE config C2: 10M x 64, k = 256).
 //
-// Per 128-row tile of X the kernel computes  S = X . (-2 C)^T  as a 3xTF32 split product
-//     S = Xhi.Bhi + Xhi.Blo + Xlo.Bhi          (B = -2C,  hi = tf32 part, lo = fp32 remainder)
-// which carries ~2^-21 relative error per product (fp32-GEMM class accuracy) instead of TF32's
-// 2^-11, so that labels agree with the reference's float64 E-step
-// (sklearn pairwise_distances_argmin_min, dask_ml/metrics/pairwise.py:35-38) except on near-ties.
-//   * X tiles arrive by TMA (SWIZZLE_128B, K-major) into a 3-stage shared-memory ring and are
-//     used as the A operand directly (the tensor core consumes the upper 19 bits = Xhi);
-//   * Xlo = X - Xhi is produced by the epilogue warps from the same smem tile and stored to
-//     TMEM (tcgen05.st); the third product takes A from TMEM;
-//   * B tiles (hi and lo, K-major SWIZZLE_128B) are loaded once per CTA and stay resident;
-//   * accumulators live in TMEM, two 128-column buffers ping-pong between the MMA issuer and the
-//     epilogue (a tile of k<=256 centres is processed as two "units" of <=128 columns);
-//   * epilogue: tcgen05.ld -> +||c||^2 -> running arg-min per row (lowest index wins ties),
-//     exact fp32 re-evaluation of the winning distance, label store;
-//   * M-step (_centers_dense, dask_ml/cluster/k_means.py:572-582): the smem-resident X tile is
-//     scatter-added into REGISTER-resident per-CTA sums: warp w owns clusters {w, w+8, ...},
-//     lane l owns features {l, l+32}; no atomics, no second read of X from HBM.
+// Per 128-row tile of X the kernel computes  acc = ||c||^2 + X . (-2 C)^T  with the product as a 3xTF32 split
+//     Xhi.Bhi + Xhi.Blo + Xlo.Bhi          (B = -2C,  hi = tf32 part, lo = fp32 remainder)
+// (~2^-21 relative error per product, fp32-GEMM class, instead of TF32's 2^-11) so that labels agree with the
+// reference's float64 E-step (sklearn pairwise_distances_argmin_min, dask_ml/metrics/pairwise.py:35-38) except
+// on near-ties, which are re-decided in float64; ||c||^2 enters through one extra K-step (rows [hi,mid,lo,0..]
+// against a constant [1,1,1,0..] tile).  The M-step (_centers_dense, dask_ml/cluster/k_means.py:572-582) is
+// fused: rows are scatter-added into REGISTER-resident per-CTA sums, X is read from HBM once.
 //
-// Warp roles (640 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle
-//                           4-7 and 8-11 Xlo converter + epilogue, alternate tiles (thread == row == TMEM lane)
-//                           12-19 distance + M-step
+// Warp roles (896 threads):
+//   0       TMA producer of the A ring (2 x 128-row X tiles, SWIZZLE_128B K-major) + L2 prefetch ahead
+//   1       MMA issuer (warp-converged, uniform-register operands, one elected lane issues tcgen05.mma/commit)
+//   2       TMEM allocator (512 columns: 3 x 128 accumulator buffers + 2 x 64 Xlo)
+//   3       TMA producer of the M ring (2 x 32-row quarter tiles re-fetched from L2 for the M-step warps)
+//   4-7, 8-11   two Xlo-converter + epilogue warp sets on alternate tiles (thread == row == TMEM lane)
+//   12-27   16 distance + M-step warps (warp w owns clusters c % 16 == w; lane l holds features l, l+32)
+// Pipelines (mbarriers): A ring full/empty (empty is released by tcgen05.commit), accumulator full/empty per
+// (epilogue set, buffer), Xlo full, labels full/empty, M ring full/empty.  DESIGN.md has the full description.
 #include "bkm_common.cuh"
 #include <cuda.h>
 #include <math_constants.h>
