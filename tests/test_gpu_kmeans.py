@@ -220,3 +220,30 @@ def test_check_estimator():
         res = check_estimator(KMeans(), on_fail=None)
     bad = [(r["check_name"], str(r["exception"])[:200]) for r in res if r["status"] == "failed"]
     assert not bad, bad
+
+
+REF_CASES = ["ref_lloyd_f32_64x256", "ref_lloyd_f64_16x8", "ref_lloyd_f32_41x100", "ref_lloyd_f32_13x20_conv"]
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_engine_matches_fixtures_written_by_the_reference(name):
+    """The CUDA engine against outputs of the UNMODIFIED reference code (tests/golden/ref_shim.py): same
+    n_iter, labels (modulo float64 near-ties), centres, inertia (both Q4 branches), predict and transform."""
+    import os
+
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    X = ChunkedArray.from_array(g["X"], int(g["chunks"]))
+    km = KMeans(int(g["k"]), init=g["init"], max_iter=int(g["max_iter"]), tol=float(g["tol"])).fit(X)
+    assert km.n_iter_ == int(g["n_iter"])
+    np.testing.assert_allclose(km.cluster_centers_, g["centers"], rtol=2e-5, atol=2e-5)
+    assert km.cluster_centers_.dtype == g["centers"].dtype
+    assert_labels_match(km.labels_.compute(), g["labels"], g["X"], g["centers"], rtol=1e-6)
+    np.testing.assert_allclose(km.inertia_, float(g["inertia"]), rtol=1e-6)
+    km.cluster_centers_ = g["centers"]
+    assert_labels_match(km.predict(X).compute(), g["predict"], g["X"], g["centers"], rtol=1e-6)
+    tr = km.transform(X).compute()[:256]
+    scale = np.sqrt((g["X"][:256].astype(np.float64) ** 2).sum(1)[:, None] + (g["centers"].astype(np.float64) ** 2).sum(1)[None])
+    assert np.max(np.abs(tr - g["transform"]) / scale) < (2e-3 if g["X"].dtype == np.float32 else 1e-9)

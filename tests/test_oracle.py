@@ -154,3 +154,36 @@ def test_golden_fixtures(oracle, name):
     np.testing.assert_array_equal(np.concatenate(lab), g["labels"])
     np.testing.assert_allclose(C, g["centers"], rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(inertia, float(g["inertia"]), rtol=1e-12)
+
+
+REF_CASES = ["ref_lloyd_f32_64x256", "ref_lloyd_f64_16x8", "ref_lloyd_f32_41x100", "ref_lloyd_f32_13x20_conv"]
+
+
+@pytest.mark.parametrize("name", REF_CASES)
+def test_oracle_reproduces_the_reference_itself(oracle, name):
+    """Fixtures written by tests/golden/ref_shim.py, i.e. by the UNMODIFIED reference source files
+    (dask_ml/cluster/k_means.py, metrics/pairwise.py, utils.py) executed over an eager stand-in for dask:
+    KMeans(init=ndarray).fit -> labels_, cluster_centers_, inertia_, n_iter_.  The oracle must agree bit for bit
+    on labels / n_iter and to float64 round-off on centres and inertia (both inertia branches of Q4 occur)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    blocks = oracle.to_blocks(g["X"], int(g["chunks"]))
+    lab, inertia, C, n_iter = oracle.kmeans_single_lloyd(blocks, int(g["k"]), init=g["init"],
+                                                        max_iter=int(g["max_iter"]), tol=float(g["tol"]))
+    assert n_iter == int(g["n_iter"])
+    np.testing.assert_array_equal(np.concatenate(lab), g["labels"])
+    assert np.concatenate(lab).dtype == g["labels"].dtype == np.int32
+    np.testing.assert_allclose(C, g["centers"], rtol=1e-13, atol=0)
+    assert C.dtype == g["centers"].dtype
+    np.testing.assert_allclose(inertia, float(g["inertia"]), rtol=1e-13)
+    tr = np.concatenate(oracle.euclidean_distances(blocks, g["centers"]))[:256]
+    np.testing.assert_allclose(tr, g["transform"], rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_pairwise_ops_vs_reference(oracle):
+    """dask_ml.metrics.pairwise_distances_argmin_min / pairwise_distances run by the reference code itself."""
+    g = np.load(os.path.join(GOLD, "ref_pairwise_ops.npz"))
+    blocks = oracle.to_blocks(g["X"], 500)
+    a, b = oracle.pairwise_distances_argmin_min(blocks, g["centers"])
+    np.testing.assert_array_equal(np.concatenate(a), g["argmin"])
+    np.testing.assert_allclose(np.concatenate(b), g["mins"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(np.concatenate(oracle.pairwise_distances(blocks, g["centers"])), g["dists"], atol=1e-12)
