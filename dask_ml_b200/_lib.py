@@ -44,6 +44,7 @@ SIGNATURES = {
     "bkm_launch_count": (_i64, []),
     "bkm_debug_abort_code": (ctypes.c_uint, []),
     "bkm_debug_abort_detail": (None, [_c_void_p]),
+    "bkm_debug_trace": (_int, [_c_void_p, _int]),
 }
 
 _lib = None

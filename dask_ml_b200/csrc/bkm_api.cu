@@ -218,5 +218,6 @@ int64_t bkm_launch_count(void) { return (int64_t)g_launches; }
 
 unsigned int bkm_debug_abort_code(void) { return bkm::tc_abort_code(); }
 void bkm_debug_abort_detail(unsigned int* out64_host) { bkm::tc_abort_detail(out64_host); }
+int bkm_debug_trace(long long* out_host, int n) { return bkm::tc_trace(out_host, n); }
 
 }  // extern "C"

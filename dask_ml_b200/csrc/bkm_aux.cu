@@ -2,6 +2,7 @@
 // reduction of per-CTA partials, centre update + shift, k-means|| sampling, transform, NaN scan.
 #include "bkm_common.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 
 namespace bkm {
 
@@ -11,7 +12,7 @@ long long g_launches = 0;
 // pack_centers: float64 centres [k][d] -> every layout the kernels read (see PackLayout).
 //   cT   [k][d4]  x-dtype, zero padded          cnT  [k] x-dtype   ||c||^2 (computed in f64)
 //   c64  [k][d]   float64 copy                  cn64 [k] float64
-//   bhi  [kp][dk] fp32: tf32-rounded (-2 c)     blo  [kp][dk] fp32: (-2 c) - bhi
+//   bhi  [kp][64] fp16: rn(-2 s c)              blo  [kp][64] fp16: rn(-2 s c - bhi)   (s = header scale)
 //   cn32 [kp]     fp32 ||c||^2, +inf for padded centres
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float to_tf32_rna(float x) {
@@ -32,17 +33,22 @@ __global__ void pack_centers_kernel(const double* __restrict__ C, unsigned char*
       int r = i / L.d4, c = i - r * L.d4;
       cT[i] = c < d ? (float)C[(size_t)r * d + c] : 0.f;
     }
-    float* bhi = reinterpret_cast<float*>(pack + L.off_bhi);
-    float* blo = reinterpret_cast<float*>(pack + L.off_blo);
-    for (int i = tid; i < L.kp * L.dk; i += nth) {
-      int r = i / L.dk, c = i - r * L.dk;
-      float hi = 0.f, lo = 0.f;
-      if (r < k && c < d) {
-        double v = -2.0 * C[(size_t)r * d + c];
-        hi = to_tf32_rna((float)v);
-        lo = (float)(v - (double)hi);
+    // tcgen05 operands: B = -2 s C as an fp16 pair (hi + lo carries 22 significant bits); rows/columns
+    // beyond (k, d) are zero.  Only shapes the tensor path takes (d <= 64) have room in the pack.
+    if (d <= L.dh) {
+      const double sc = (double)reinterpret_cast<const PackHeader*>(pack)->scale;
+      __half* bhi = reinterpret_cast<__half*>(pack + L.off_bhi);
+      __half* blo = reinterpret_cast<__half*>(pack + L.off_blo);
+      for (int i = tid; i < L.kp * L.dh; i += nth) {
+        int r = i / L.dh, c = i - r * L.dh;
+        __half hi = __float2half_rn(0.f), lo = hi;
+        if (r < k && c < d) {
+          const double v = -2.0 * sc * C[(size_t)r * d + c];
+          hi = __double2half(v);
+          lo = __double2half(v - (double)__half2float(hi));
+        }
+        bhi[i] = hi; blo[i] = lo;
       }
-      bhi[i] = hi; blo[i] = lo;
     }
   } else {
     double* cT = reinterpret_cast<double*>(pack + L.off_cT);
@@ -79,7 +85,8 @@ __global__ void pack_norms_kernel(const double* __restrict__ C, unsigned char* p
         float* bcn = reinterpret_cast<float*>(pack + L.off_bcn) + (j >> 3) * 64 + (j & 7) * 4;
         float hi = 3.0e38f, mid = 0.f, lo = 0.f;
         if (j < k) {
-          const float cf = (float)s;
+          const double sc = (double)reinterpret_cast<const PackHeader*>(pack)->scale;
+          const float cf = (float)(s * sc * sc);          // the tensor path works on s X and s C
           hi = to_tf32_rna(cf);
           const float r1 = cf - hi;
           mid = to_tf32_rna(r1);
@@ -89,6 +96,28 @@ __global__ void pack_norms_kernel(const double* __restrict__ C, unsigned char* p
         bcn[32] = 0.f; bcn[33] = 0.f; bcn[34] = 0.f; bcn[35] = 0.f;
       }
     }
+  }
+}
+
+// scale = 2^(9 - floor(log2 max|c|)): s * max|c| in [2^9, 2^10), so -2 s c fits fp16 with a 32x margin and
+// rows of X up to ~64x the largest centre component convert without overflow (larger ones are deferred to
+// the float64 path by the kernel).  Runs first: the other pack kernels read it.
+__global__ void pack_scale_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L) {
+  __shared__ double sm[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < L.k * L.d; i += blockDim.x) m = fmax(m, fabs(C[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sm[w]);
+    int e = 0;
+    if (m > 0.0 && m < CUDART_INF) e = 9 - ilogb(m);
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    PackHeader* h = reinterpret_cast<PackHeader*>(pack);
+    h->scale = (float)scalbn(1.0, e);
+    h->pad2 = 0.f;
   }
 }
 
@@ -111,11 +140,12 @@ __global__ void pack_header_kernel(unsigned char* pack, PackLayout L) {
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s) {
   PackLayout L = pack_layout(k, d, dtype);
   int nb = (L.kp * L.dk + 255) / 256; if (nb > 296) nb = 296; if (nb < 1) nb = 1;
+  pack_scale_kernel<<<1, 1024, 0, s>>>(C, (unsigned char*)pack, L);
   pack_centers_kernel<<<nb, 256, 0, s>>>(C, (unsigned char*)pack, L);
   int nb2 = (L.kp + 7) / 8; if (nb2 > 148) nb2 = 148;
   pack_norms_kernel<<<nb2, 256, 0, s>>>(C, (unsigned char*)pack, L);
   pack_header_kernel<<<1, 256, 0, s>>>((unsigned char*)pack, L);
-  note_launch(3);
+  note_launch(4);
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;
 }

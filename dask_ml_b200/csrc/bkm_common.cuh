@@ -29,6 +29,7 @@ struct PackLayout {
   int d4;      // d rounded up to a multiple of 4 (SIMT row pitch, zero padded)
   int kp;      // k rounded up to a multiple of 16 (UMMA N granularity)
   int dk;      // d rounded up to a multiple of 32 (one 128-byte swizzle atom of fp32 per K-block)
+  int dh;      // row length of the fp16 MMA operand tiles: 64 halves = one 128-byte swizzle atom (d <= 64)
   size_t esz;  // sizeof(T)
   size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, off_bcn, total;
 };
@@ -39,14 +40,15 @@ static inline PackLayout pack_layout(int k, int d, int dtype) {
   L.d4 = (d + 3) / 4 * 4;
   L.kp = (k + 15) / 16 * 16;
   L.dk = (d + 31) / 32 * 32;
+  L.dh = 64;
   L.esz = dtype == BKM_F64 ? 8 : 4;
   size_t o = 256;  // header
   L.off_cT = o;   o = align_up(o + (size_t)k * L.d4 * L.esz, 256);
   L.off_cnT = o;  o = align_up(o + (size_t)k * L.esz, 256);
   L.off_c64 = o;  o = align_up(o + (size_t)k * d * 8, 256);
   L.off_cn64 = o; o = align_up(o + (size_t)k * 8, 256);
-  L.off_bhi = o;  o = align_up(o + (size_t)L.kp * L.dk * 4, 256);
-  L.off_blo = o;  o = align_up(o + (size_t)L.kp * L.dk * 4, 256);
+  L.off_bhi = o;  o = align_up(o + (size_t)L.kp * L.dh * 2, 256);   // fp16 tiles (tcgen05 path, d <= 64)
+  L.off_blo = o;  o = align_up(o + (size_t)L.kp * L.dh * 2, 256);
   L.off_cn32 = o; o = align_up(o + (size_t)L.kp * 4, 256);
   L.off_bcn = o;  o = align_up(o + (size_t)L.kp * 32, 256);   // ||c||^2 as an MMA operand tile (see bkm_tc.cu)
   L.total = o;
@@ -57,6 +59,8 @@ static inline PackLayout pack_layout(int k, int d, int dtype) {
 struct PackHeader {
   int k, d, dtype, pad;
   double cn_max;   // max_j ||c_j||^2 (float64) — used by the near-tie margin bound
+  float scale;     // power of two s with s * max|c_ji| in [2^9, 2^10): the tcgen05 path multiplies X and C by s
+  float pad2;      // before the fp16 split, so that both fit fp16's range (exact: only exponents change)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -110,6 +114,7 @@ int launch_simt(const ChunkArgs& a, bool mstep, int dtype, int sm_count, int* gr
 // implemented in bkm_tc.cu
 bool tc_supported(int d, int k, int dtype);
 int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
+int tc_trace(long long* out, int n);
 // implemented in bkm_aux.cu
 int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
                            double* sums, long long* counts, double* dist_sum, cudaStream_t s);

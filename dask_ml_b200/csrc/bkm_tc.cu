@@ -2,60 +2,74 @@
 //
 // Shapes: fp32 X with d % 4 == 0, d <= 64, k <= 256 (BASELINE config C2: 10M x 64, k = 256).
 //
-// Per 128-row tile of X the kernel computes  acc = ||c||^2 + X . (-2 C)^T  with the product as a 3xTF32 split
-//     Xhi.Bhi + Xhi.Blo + Xlo.Bhi          (B = -2C,  hi = tf32 part, lo = fp32 remainder)
-// (~2^-21 relative error per product, fp32-GEMM class, instead of TF32's 2^-11) so that labels agree with the
-// reference's float64 E-step (sklearn pairwise_distances_argmin_min, dask_ml/metrics/pairwise.py:35-38) except
-// on near-ties, which are re-decided in float64; ||c||^2 enters through one extra K-step (rows [hi,mid,lo,0..]
+// Per 128-row tile of X the kernel computes  acc = s^2 ||c||^2 + (s X) . (-2 s C)^T  with the product as a
+// split-fp16 triple on the kind::f16 tensor pipe (twice the TF32 rate):
+//     Xhi.Bhi + Xhi.Blo + Xlo.Bhi        (hi = rn_fp16(v), lo = rn_fp16(v - hi): 22 significant bits)
+// s is a power of two chosen from the centres (PackHeader::scale) so that both operands sit in fp16's range;
+// scaling by s is exact, so the result is the fp32-GEMM-class distance (~2^-22 relative error per product)
+// and labels agree with the reference's float64 E-step (sklearn pairwise_distances_argmin_min,
+// dask_ml/metrics/pairwise.py:35-38) except on near-ties, which are re-decided in float64 (as are rows whose
+// scaled entries leave fp16's range).  ||c||^2 enters through one extra tf32 K-step (rows [hi,mid,lo,0..]
 // against a constant [1,1,1,0..] tile).  The M-step (_centers_dense, dask_ml/cluster/k_means.py:572-582) is
 // fused: rows are scatter-added into REGISTER-resident per-CTA sums, X is read from HBM once.
 //
 // Warp roles (896 threads):
-//   0       TMA producer of the A ring (2 x 128-row X tiles, SWIZZLE_128B K-major) + L2 prefetch ahead
+//   0       TMA producer of the A ring (NST x 128-row fp32 X tiles, SWIZZLE_128B) + L2 prefetch ahead
 //   1       MMA issuer (warp-converged, uniform-register operands, one elected lane issues tcgen05.mma/commit)
-//   2       TMEM allocator (512 columns: 3 x 128 accumulator buffers + 2 x 64 Xlo)
-//   3       TMA producer of the M ring (2 x 32-row quarter tiles re-fetched from L2 for the M-step warps)
-//   4-7, 8-11   two Xlo-converter + epilogue warp sets on alternate tiles (thread == row == TMEM lane)
+//   2       TMEM allocator (512 columns: 3 x 128 accumulator buffers + 2 x (32 Xhi + 32 Xlo))
+//   3       [ring mode only] TMA producer of the M ring (32-row quarter tiles re-fetched from L2)
+//   4-7, 8-11   two converter + epilogue warp sets on alternate tiles (thread == row == TMEM lane)
 //   12-27   16 distance + M-step warps (warp w owns clusters c % 16 == w; lane l holds features l, l+32)
-// Pipelines (mbarriers): A ring full/empty (empty is released by tcgen05.commit), accumulator full/empty per
-// (epilogue set, buffer), Xlo full, labels full/empty, M ring full/empty.  DESIGN.md has the full description.
+// The M-step warps read the rows either straight from the A ring (direct mode: the ring is >= 4 stages deep,
+// a stage is released by the converter set AND the 16 M-step warps) or, when shared memory is short (the
+// distance variants keep an fp32 copy of the centres), from a small separate ring.
+// Pipelines (mbarriers): A ring full/empty, accumulator full/empty per (epilogue set, buffer), X operands
+// in TMEM full, labels full/empty, M ring full/empty.  DESIGN.md has the full description.
 #include "bkm_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 namespace bkm {
 
 static const int BM = 128;           // rows per tile
-static const int NMW = 16;               // distance + M-step warps (each owns the clusters c % NMW == its index)
-static const int TC_THREADS = (12 + NMW) * 32;
+static const int NMW = 16;               // distance variants: 16 distance + M-step warps (warp owns the clusters c % 16)
+static const int NMW_LANE = 8;           // pure Lloyd variant: 8 M-step warps, LANE j of warp w owns cluster 32 w + j
+static const int LIST_BYTES = 256 * 4 + BM * 4;   // per label buffer: head[256] + next[128] (row lists per cluster)
+__host__ __device__ constexpr int tc_mwarps(bool mstep, bool want_dist) { return (mstep && !want_dist) ? NMW_LANE : NMW; }
+__host__ __device__ constexpr int tc_threads(bool mstep, bool want_dist) { return (12 + tc_mwarps(mstep, want_dist)) * 32; }
 static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
 static const int MH = 32;                 // rows per M-ring stage (a quarter tile)
 static const int MKBLK_BYTES = MH * 128;
 
 struct TcCfg {
-  int KB;        // 32-float K-blocks per row (1 or 2)
-  int KS;        // MMA K-steps of 8 (ceil(d/8))
+  int KB;        // 32-float K-blocks per row of the fp32 X tiles (1 or 2)
+  int KS;        // MMA K-steps of 16 (ceil(d/16))
   int NP;        // padded centre count (multiple of 16, <= 256)
   int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
   int U;
   int NST;       // X stages
-  uint32_t off_bhi, off_blo, off_bcn, off_ones, off_x, off_m, off_cn, off_lab, off_flist, off_red, off_bar, off_tptr, total;
+  int direct;    // 1: the M-step warps read the A ring; 0: separate M ring
+  uint32_t off_bhi, off_blo, off_bcn, off_ones, off_c32, off_x, off_m, off_lab, off_red, off_bar, off_tptr, total;
 };
 
-static const int NBUF = 3;               // 128-column TMEM accumulator buffers (3*128 + 2*64 Xlo = 512 columns)
+static const int NBUF = 3;               // 128-column TMEM accumulator buffers (3*128 acc + 2*(32 Xhi + 32 Xlo) = 512)
+static const int NSTMAX = 6;             // A ring stages (barrier slots)
+static const int NLAB = 4;               // label buffers between the epilogue sets and the M-step warps
+static const uint32_t TM_XHI = 384, TM_XLO = 448;   // TMEM columns of the fp16 X operands (+ (tile & 1) * 32)
 
 enum {
   BAR_B_FULL = 0,
-  BAR_X_FULL = 1,       // [NST<=4]
-  BAR_X_EMPTY = 5,      // [4]
-  BAR_ACC_FULL = 9,     // [set 2][buf 3]  one barrier per (epilogue warp set, accumulator buffer): every
-  BAR_ACC_EMPTY = 15,   // [set 2][buf 3]  waiter then observes consecutive phases (no parity aliasing)
-  BAR_XLO_FULL = 21,    // [2]
-  BAR_LAB_FULL = 23,    // [2]
-  BAR_LAB_EMPTY = 25,   // [2]
-  BAR_M_FULL = 27,      // [2]  M ring: 64-row half tiles re-fetched (L2 hits) for the M-step warps
-  BAR_M_EMPTY = 29,     // [2]
-  BAR_COUNT = 31
+  BAR_X_FULL = 1,                          // [NSTMAX]
+  BAR_X_EMPTY = BAR_X_FULL + NSTMAX,       // [NSTMAX]
+  BAR_ACC_FULL = BAR_X_EMPTY + NSTMAX,     // [set 2][buf 3]  one barrier per (epilogue warp set, accumulator buffer): every
+  BAR_ACC_EMPTY = BAR_ACC_FULL + 6,        // [set 2][buf 3]  waiter then observes consecutive phases (no parity aliasing)
+  BAR_XOP_FULL = BAR_ACC_EMPTY + 6,        // [2]   X operands of tile (it & 1) are in TMEM
+  BAR_LAB_FULL = BAR_XOP_FULL + 2,         // [NLAB]
+  BAR_LAB_EMPTY = BAR_LAB_FULL + NLAB,     // [NLAB]
+  BAR_M_FULL = BAR_LAB_EMPTY + NLAB,       // [2]  M ring (ring mode): 32-row quarter tiles re-fetched (L2 hits)
+  BAR_M_EMPTY = BAR_M_FULL + 2,            // [2]
+  BAR_COUNT = BAR_M_EMPTY + 2
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -66,6 +80,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // (set, buffer), mod 2.  The pattern repeats every lcm(2U, 3) units: U=1 -> each pair once per 6 units,
 // U=2 -> twice per 12 units (second occurrences: g % 12 in {4,6,8,9,10,11}).
 __device__ __forceinline__ uint32_t acc_parity(long long g, int U) {
+  if (NBUF == 2) return (uint32_t)((U == 1 ? (g >> 1) : (g >> 2)) & 1);     // each (set, buffer) pair: every 2U-th unit
   if (U == 1) return (uint32_t)((g / 6) & 1);
   return (uint32_t)((0xF50u >> (int)(g % 12)) & 1u);
 }
@@ -82,6 +97,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // warp) in g_tc_abort and returns; every later wait returns at once, the kernel drains with garbage and
 // the host reports the code (bkm_debug_abort_code).
 __device__ unsigned int g_tc_abort = 0;
+#ifndef BKM_TRACE
+#define BKM_TRACE 0
+#endif
+// Pipeline timeline of CTA 0 (debug builds, `make TRACE=1`): SM clock of event `slot` for its first 128 tiles.
+#if BKM_TRACE
+__device__ long long g_tc_trace[16 * 128];
+#define TRACE(slot, it) do { if (blockIdx.x == 0 && (it) < 128) g_tc_trace[(slot) * 128 + (int)(it)] = clock64(); } while (0)
+#else
+#define TRACE(slot, it) do { } while (0)
+#endif
 __device__ unsigned int g_tc_dbg[64];     // per-warp abort code of the first CTA that aborts (debug)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -108,7 +133,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done) __nanosleep(128);
+    if (!done) __nanosleep(256);
     if (spin > (1u << 20) || ((spin & 255) == 255 && *(volatile unsigned int*)&g_tc_abort)) {
       atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
       return;
@@ -147,10 +172,11 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// A (128 rows x 16 fp16 = 8 TMEM columns, two K elements per 32-bit column) from TMEM, B from shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 #define TC_LD16(taddr, r)                                                                              \
@@ -160,15 +186,14 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
                  "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),            \
                  "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                                                 \
                : "r"(taddr) : "memory")
-#define TC_ST32(taddr, r)                                                                              \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                         \
-               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                              \
-               "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                     \
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),         \
-                 "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),       \
-                 "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),   \
-                 "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),   \
-                 "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
+// 16 columns from r[o], r[o+2], ..., r[o+30]
+#define TC_ST16S(taddr, r, o)                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                         \
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                             \
+               ::"r"(taddr), "r"(r[o + 0]), "r"(r[o + 2]), "r"(r[o + 4]), "r"(r[o + 6]), "r"(r[o + 8]), \
+                 "r"(r[o + 10]), "r"(r[o + 12]), "r"(r[o + 14]), "r"(r[o + 16]), "r"(r[o + 18]),       \
+                 "r"(r[o + 20]), "r"(r[o + 22]), "r"(r[o + 24]), "r"(r[o + 26]), "r"(r[o + 28]),       \
+                 "r"(r[o + 30]) : "memory")
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
 // 8-row x 128-byte swizzle atoms, SBO = 1024 B between atoms along M/N, LBO unused (1).
@@ -181,9 +206,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc(int n) {
+// instruction descriptors: fp32 accumulate, A and B K-major, M = 128, N = n; operand format 2 = tf32, 0 = fp16
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 // byte offset of 16-byte chunk q (0..7) of row r inside one swizzled K-block
 __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4)); }
@@ -191,22 +219,26 @@ __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r
 #define ACC32_CASE(j) case j: acc[j][0] += x0; acc[j][1] += x1; break;
 
 template <bool MSTEP, bool WANT_DIST>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(MSTEP, WANT_DIST), 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
                 const __grid_constant__ CUtensorMap tm_xm) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr bool LANE_OWNS = MSTEP && !WANT_DIST;     // M-step flavour (see the two M-step blocks below)
+  constexpr int NMWK = tc_mwarps(MSTEP, WANT_DIST);
+  constexpr int NTHREADS = tc_threads(MSTEP, WANT_DIST);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
   if (tid == 0 && (sbase & 1023)) __trap();
   const uint32_t s_bhi = sbase + cfg.off_bhi, s_blo = sbase + cfg.off_blo, s_x = sbase + cfg.off_x;
-  int* lab_s = reinterpret_cast<int*>(smem + cfg.off_lab);          // [2][BM]
-  double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [5]
+  int* lab_s = reinterpret_cast<int*>(smem + cfg.off_lab);          // [NLAB][BM]
+  double* red_s = reinterpret_cast<double*>(smem + cfg.off_red);    // [NMW + 1]
   const uint32_t bars = sbase + cfg.off_bar;
   uint32_t* tptr_s = reinterpret_cast<uint32_t*>(smem + cfg.off_tptr);
 #define BAR(i) (bars + 8u * (uint32_t)(i))
 
   const int NST = cfg.NST, KB = cfg.KB, KS = cfg.KS, NP = cfg.NP, U = cfg.U;
+  const bool direct = cfg.direct != 0;
   const uint32_t stage_bytes = (uint32_t)KB * KBLK_BYTES;
   const long long ntiles = (a.n + BM - 1) / BM;
   const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -218,9 +250,10 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo));
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_xm));
     mbar_init(BAR(BAR_B_FULL), 1);
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < NSTMAX; ++s) {
       mbar_init(BAR(BAR_X_FULL + s), 1);
-      mbar_init(BAR(BAR_X_EMPTY + s), 1);
+      // a stage is released by the 128 converter threads of a set and, in direct mode, the M-step warps
+      mbar_init(BAR(BAR_X_EMPTY + s), direct ? 128 + NMWK : 128);
     }
     for (int b = 0; b < 2 * NBUF; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
@@ -228,12 +261,14 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(BAR_M_FULL + b), 1);
-      mbar_init(BAR(BAR_M_EMPTY + b), NMW);
-      mbar_init(BAR(BAR_XLO_FULL + b), 128);
-      mbar_init(BAR(BAR_LAB_FULL + b), 128);
-      mbar_init(BAR(BAR_LAB_EMPTY + b), NMW);
+      mbar_init(BAR(BAR_M_EMPTY + b), NMWK);
+      mbar_init(BAR(BAR_XOP_FULL + b), 128);
     }
-    red_s[NMW] = 0.0;
+    for (int b = 0; b < NLAB; ++b) {
+      mbar_init(BAR(BAR_LAB_FULL + b), 128);
+      mbar_init(BAR(BAR_LAB_EMPTY + b), NMWK);
+    }
+    red_s[NMWK] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -241,16 +276,31 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   {
-    // ||c||^2 enters the accumulator through one extra MMA K-step: B rows [hi,mid,lo,0,...] (exact 3-way
-    // tf32 split, built by pack_norms_kernel) against a constant A tile of rows [1,1,1,0,...]; both tiles
-    // use the canonical no-swizzle K-major layout (8-row groups of 256 B).  Plain stores + proxy fence.
+    // s^2 ||c||^2 enters the accumulator through one extra tf32 MMA K-step: B rows [hi,mid,lo,0,...] (exact
+    // 3-way tf32 split, built by pack_norms_kernel) against a constant A tile of rows [1,1,1,0,...]; both
+    // tiles use the canonical no-swizzle K-major layout (8-row groups of 256 B).  Plain stores + proxy fence.
     const float4* g = reinterpret_cast<const float4*>(a.pack + a.L.off_bcn);
     float4* sdst = reinterpret_cast<float4*>(smem + cfg.off_bcn);
-    for (int i = tid; i < NP * 2; i += TC_THREADS) sdst[i] = g[i];
+    for (int i = tid; i < NP * 2; i += NTHREADS) sdst[i] = g[i];
     float4* odst = reinterpret_cast<float4*>(smem + cfg.off_ones);
-    for (int i = tid; i < BM * 2; i += TC_THREADS)
+    for (int i = tid; i < BM * 2; i += NTHREADS)
       odst[i] = ((i >> 3) & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(1.f, 1.f, 1.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (LANE_OWNS) {
+      // row lists: every head starts empty
+      int* hd = reinterpret_cast<int*>(smem + cfg.off_lab);
+      for (int i = tid; i < NLAB * (LIST_BYTES / 4); i += NTHREADS) hd[i] = -1;
+    }
+    if (WANT_DIST) {
+      // fp32 centres [NP][KB*32] for the exact direct-form winning distance (rows >= k / columns >= d: zero)
+      const float* gc = reinterpret_cast<const float*>(a.pack + a.L.off_cT);      // [k][d4]
+      float* cdst = reinterpret_cast<float*>(smem + cfg.off_c32);
+      const int pitch = KB * 32;
+      for (int i = tid; i < NP * pitch; i += NTHREADS) {
+        const int j = i / pitch, c = i - j * pitch;
+        cdst[i] = (j < a.k && c < a.d) ? gc[(size_t)j * a.L.d4 + c] : 0.f;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -260,11 +310,9 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      mbar_expect_tx(BAR(BAR_B_FULL), 2u * (uint32_t)KB * (uint32_t)NP * 128u);
-      for (int kb = 0; kb < KB; ++kb) {
-        tma_load_2d(s_bhi + (uint32_t)kb * NP * 128u, &tm_bhi, BAR(BAR_B_FULL), kb * 32, 0);
-        tma_load_2d(s_blo + (uint32_t)kb * NP * 128u, &tm_blo, BAR(BAR_B_FULL), kb * 32, 0);
-      }
+      mbar_expect_tx(BAR(BAR_B_FULL), 2u * (uint32_t)NP * 128u);
+      tma_load_2d(s_bhi, &tm_bhi, BAR(BAR_B_FULL), 0, 0);
+      tma_load_2d(s_blo, &tm_blo, BAR(BAR_B_FULL), 0, 0);
       const int PF = 6;        // L2 prefetch distance (tiles) ahead of the shared-memory ring
       for (long long it = 0; it < PF && it < my_tiles; ++it)
         for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((blockIdx.x + it * gridDim.x) * BM));
@@ -276,6 +324,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         if (it + PF < my_tiles)
           for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((tile + (long long)PF * gridDim.x) * BM));
         mbar_wait(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
+        TRACE(0, it);
         mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
         for (int kb = 0; kb < KB; ++kb)
           tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
@@ -283,11 +332,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       }
     }
   } else if (warp == 3) {
-    // =========================== TMA producer of the M ring ===========================
-    // Re-fetches every tile as two 64-row halves for the M-step / distance warps.  The same rows were
+    // =========================== TMA producer of the M ring (ring mode) ===========================
+    // Re-fetches every tile as four 32-row quarters for the M-step / distance warps.  The same rows were
     // loaded for the MMA a few microseconds earlier, so these are L2 hits: HBM traffic stays at one read
-    // of X per iteration while the M-step no longer holds the MMA's shared-memory stages.
-    if (lane == 0) {
+    // of X per iteration while the M-step does not hold the (short) A ring.
+    if (lane == 0 && !direct) {
       const uint32_t s_m = sbase + cfg.off_m;
       const uint32_t mbytes = (uint32_t)KB * MKBLK_BYTES;
 #pragma unroll 1
@@ -309,19 +358,16 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     mbar_wait(BAR(BAR_B_FULL), 0);
     tc_fence_after();
     const uint64_t dflags = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    const uint32_t bblk = (uint32_t)NP * 128u;          // bytes of one K-block of a B tile
     // no-swizzle K-major operands of the ||c||^2 K-step: LBO = 128 B (second 16-byte K chunk), SBO = 256 B
     const uint64_t dns = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint64_t dcn = dns | (uint64_t)(((sbase + cfg.off_bcn) >> 4) & 0x3FFF);
     const uint64_t dones = dns | (uint64_t)(((sbase + cfg.off_ones) >> 4) & 0x3FFF);
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
-      const int stage = (int)(it % NST);
-      const uint32_t ph = (uint32_t)((it / NST) & 1);
-      const uint32_t xs = s_x + stage * stage_bytes;
-      const uint32_t xlo_t = tmem + 384u + (uint32_t)(it & 1) * 64u;
-      mbar_wait(BAR(BAR_X_FULL + stage), ph);
-      tc_fence_after();
+      // Both X operands live in TMEM (fp16 pairs written by the converter): only the 4 KB B slice of each
+      // K-step is fetched from shared memory.
+      const uint32_t xhi_t = tmem + TM_XHI + (uint32_t)(it & 1) * 32u;
+      const uint32_t xlo_t = tmem + TM_XLO + (uint32_t)(it & 1) * 32u;
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const long long g = it * U + u;
@@ -331,65 +377,46 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
           const long long gp = g - NBUF;
           mbar_wait(BAR(BAR_ACC_EMPTY + (int)((gp / U) & 1) * NBUF + buf), acc_parity(gp, U));
         }
+        if (u == 0) mbar_wait(BAR(BAR_XOP_FULL + (it & 1)), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
+        if (leader) TRACE(3 + 2 * u, it);
         const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
         const uint32_t rowoff = u == 0 ? 0u : (uint32_t)cfg.NU0 * 128u;
-        const uint32_t idesc = make_idesc(ncols);
+        const uint32_t idesc = make_idesc_f16(ncols);
         const uint32_t d_t = tmem + (uint32_t)buf * 128u;
-        const uint64_t da = dflags | (uint64_t)((xs >> 4) & 0x3FFF);
         const uint64_t dbh = dflags | (uint64_t)(((s_bhi + rowoff) >> 4) & 0x3FFF);
         const uint64_t dbl = dflags | (uint64_t)(((s_blo + rowoff) >> 4) & 0x3FFF);
-        // pass 1: Xhi . Bhi (A = raw fp32 tile; the tensor core reads its tf32 part), pass 2: Xhi . Blo
         if (leader) {
+          // Xhi . Bhi   (K-step s: 16 halves = 32 bytes inside the 128-byte swizzle atom, 8 TMEM columns)
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            if (s < KS) {
-              const uint32_t ao = (uint32_t)(s >> 2) * (KBLK_BYTES >> 4) + (uint32_t)(s & 3) * 2u;
-              const uint32_t bo = (uint32_t)(s >> 2) * (bblk >> 4) + (uint32_t)(s & 3) * 2u;
-              mma_tf32_ss(d_t, da + ao, dbh + bo, idesc, s > 0 ? 1u : 0u);
-            }
-          }
+          for (int s = 0; s < 4; ++s)
+            if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, s > 0 ? 1u : 0u);
+          // Xhi . Blo
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            if (s < KS) {
-              const uint32_t ao = (uint32_t)(s >> 2) * (KBLK_BYTES >> 4) + (uint32_t)(s & 3) * 2u;
-              const uint32_t bo = (uint32_t)(s >> 2) * (bblk >> 4) + (uint32_t)(s & 3) * 2u;
-              mma_tf32_ss(d_t, da + ao, dbl + bo, idesc, 1u);
-            }
-          }
-        }
-        __syncwarp();
-        if (u == 0) {
-          mbar_wait(BAR(BAR_XLO_FULL + (it & 1)), (uint32_t)((it >> 1) & 1));
-          tc_fence_after();
-        }
-        // pass 3: Xlo . Bhi   (A from TMEM)
-        if (leader) {
+          for (int s = 0; s < 4; ++s)
+            if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbl + (uint64_t)(s * 2), idesc, 1u);
+          // Xlo . Bhi
 #pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            if (s < KS) {
-              const uint32_t bo = (uint32_t)(s >> 2) * (bblk >> 4) + (uint32_t)(s & 3) * 2u;
-              mma_tf32_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + bo, idesc, 1u);
-            }
-          }
-          mma_tf32_ss(d_t, dones, dcn + (uint64_t)(rowoff >> 6), idesc, 1u);     // + ||c_j||^2
+          for (int s = 0; s < 4; ++s)
+            if (s < KS) mma_f16_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, 1u);
+          mma_tf32_ss(d_t, dones, dcn + (uint64_t)(rowoff >> 6), make_idesc_tf32(ncols), 1u);     // + s^2 ||c_j||^2
           tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * NBUF + buf));
-          // the smem stage is free once every MMA of this tile has read it (the Xlo converter finished
-          // before pass 3 could start); later consumers (M-step) read their rows from L2 instead
-          if (u == U - 1) tc_commit(BAR(BAR_X_EMPTY + stage));
+          TRACE(4 + 2 * u, it);
         }
         __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    // =========================== Xlo converter + epilogue ===========================
+    // =========================== X converter + epilogue ===========================
     // Two warp sets (warps 4-7 and 8-11) take alternate tiles, so each SM sub-partition has two epilogue
     // warps whose instruction streams interleave.  Thread == row == TMEM lane.
     const int set = (warp - 4) >> 2;
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    const float cnmax = (float)reinterpret_cast<const PackHeader*>(a.pack)->cn_max;
+    const PackHeader* hdr = reinterpret_cast<const PackHeader*>(a.pack);
+    const float sc = hdr->scale;
+    const float cnmax = (float)(hdr->cn_max * (double)sc * (double)sc);
     uint32_t xoff[8];                              // swizzled 16-byte chunk offsets of this thread's row
 #pragma unroll
     for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
@@ -398,10 +425,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     for (long long it = set; it < my_tiles; it += 2) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const int stage = (int)(it % NST);
-      // ---- convert: Xlo = X - tf32(X) -> TMEM, and ||x||^2 ----
+      // ---- convert: s X -> fp16 (hi, lo) pairs in TMEM, and ||s x||^2 ----
       float xn;
       {
         mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+        if (r == 0) TRACE(1, it);
         const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
         float xn4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -410,28 +438,59 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 t = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + xoff[q]);
-            const float e[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              xn4[i] = fmaf(e[i], e[i], xn4[i]);
-              const float hi = __uint_as_float(__float_as_uint(e[i]) & 0xFFFFE000u);
-              v[q * 4 + i] = __float_as_uint(e[i] - hi);     // exact: the 13 low mantissa bits
-            }
+            v[q * 4 + 0] = __float_as_uint(t.x); v[q * 4 + 1] = __float_as_uint(t.y);
+            v[q * 4 + 2] = __float_as_uint(t.z); v[q * 4 + 3] = __float_as_uint(t.w);
           }
-          TC_ST32(tmem + lane_addr + 384u + (uint32_t)(it & 1) * 64u + (uint32_t)kb * 32u, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = __uint_as_float(v[2 * j]) * sc, e1 = __uint_as_float(v[2 * j + 1]) * sc;
+            xn4[j & 3] = fmaf(e0, e0, xn4[j & 3]);
+            xn4[(j + 2) & 3] = fmaf(e1, e1, xn4[(j + 2) & 3]);
+            const __half2 h = __floats2half2_rn(e0, e1);          // low half = K element 2j
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);      // the subtraction is exact
+            v[2 * j] = *reinterpret_cast<const uint32_t*>(&h);
+            v[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          TC_ST16S(tmem + lane_addr + TM_XHI + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 0);
+          TC_ST16S(tmem + lane_addr + TM_XLO + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 1);
         }
         xn = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
+        mbar_arrive(BAR(BAR_X_EMPTY + stage));        // this set is done with the smem stage
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        mbar_arrive(BAR(BAR_XLO_FULL + (it & 1)));
+        mbar_arrive(BAR(BAR_XOP_FULL + (it & 1)));
+        if (r == 0) TRACE(2, it);
       }
       const float bound = a.tau * (xn + cnmax);
-      // ---- two-pass epilogue per unit ----
-      //  pass 1: m = min_j (S_j + ||c_j||^2)                      (1 FADD + 1/2 FMNMX3 per element)
-      //  pass 2: every element within `bound` of m adds (1 + j/1024) to an accumulator on the FMA pipe:
-      //          exactly one hit  -> acc = 1 + j/1024 : the arg-min, decoded exactly
-      //          two or more hits -> acc >= 2        : near-tie, the row is deferred to float64
-      float um0 = CUDART_INF_F, um1 = CUDART_INF_F, ua0 = 0.f, ua1 = 0.f;
+      // an entry beyond fp16's range (|s x| >= 65504 => xn >= 4.29e9) or a non-finite one: float64 path
+      const bool out_of_range = !(xn < 4.29e9f);
+      // ---- single-pass epilogue ----
+      // TMEM reads (64 B/cycle/SM) are the scarcest resource of this kernel, so every accumulator is read
+      // exactly once, in 16-column chunks.  Running state per row: m1 = smallest chunk minimum so far,
+      // sv[] = a copy of that chunk, m2 = smallest value seen outside it (chunk minima only: enough to
+      // decide whether anything outside the best chunk is within `bound` of m1).  After the last chunk the
+      // saved chunk is scanned once: every element within `bound` of m1 adds (1 + i/1024) to an accumulator:
+      //   exactly one hit  -> 1 + i/1024 : the arg-min, decoded exactly
+      //   two or more hits (or m2 within the bound) -> near-tie, the row is deferred to float64
+      float m1 = CUDART_INF_F, m2 = CUDART_INF_F, sbase = 0.f;
+      float sv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sv[i] = CUDART_INF_F;
+#define EPI_CHUNK(V, COLBASE)                                                            \
+  {                                                                                      \
+    const float t0 = fmin3(__uint_as_float(V[0]), __uint_as_float(V[1]), __uint_as_float(V[2]));    \
+    const float t1 = fmin3(__uint_as_float(V[3]), __uint_as_float(V[4]), __uint_as_float(V[5]));    \
+    const float t2 = fmin3(__uint_as_float(V[6]), __uint_as_float(V[7]), __uint_as_float(V[8]));    \
+    const float t3 = fmin3(__uint_as_float(V[9]), __uint_as_float(V[10]), __uint_as_float(V[11]));  \
+    const float t4 = fmin3(__uint_as_float(V[12]), __uint_as_float(V[13]), __uint_as_float(V[14])); \
+    const float cm = fminf(fmin3(t0, t1, t2), fmin3(t3, t4, __uint_as_float(V[15])));    \
+    const bool better = cm < m1;                                                         \
+    m2 = fminf(m2, fmaxf(m1, cm));                                                       \
+    m1 = fminf(m1, cm);                                                                  \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i) sv[i] = better ? __uint_as_float(V[i]) : sv[i]; \
+    sbase = better ? (float)(COLBASE) : sbase;                                           \
+  }
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const long long g = it * U + u;
@@ -440,79 +499,40 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         const int col0 = u == 0 ? 0 : cfg.NU0;
         mbar_wait(BAR(BAR_ACC_FULL + set * NBUF + buf), acc_parity(g, U));
         tc_fence_after();
+        if (r == 0) TRACE(7 + 2 * u, it);
         const uint32_t tbase = tmem + lane_addr + (uint32_t)buf * 128u;
         uint32_t v0[16], v1[16];
-        float ma = CUDART_INF_F, mb = CUDART_INF_F;
-#define EPI_MIN(V, COLBASE)                                                              \
-  {                                                                                      \
-    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float d0 = __uint_as_float(V[j4 * 4 + 0]);                                   \
-      const float d1 = __uint_as_float(V[j4 * 4 + 1]);                                   \
-      const float d2 = __uint_as_float(V[j4 * 4 + 2]);                                   \
-      const float d3 = __uint_as_float(V[j4 * 4 + 3]);                                   \
-      ma = fmin3(ma, d0, d1);                                                            \
-      mb = fmin3(mb, d2, d3);                                                            \
-    }                                                                                    \
-  }
+        // the next chunk's load is in flight while the current one is reduced
         TC_LD16(tbase, v0);
 #pragma unroll 1
         for (int c = 0; c < nch; c += 2) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (c + 1 < nch) TC_LD16(tbase + (uint32_t)(c + 1) * 16u, v1);
-          EPI_MIN(v0, col0 + c * 16)
+          EPI_CHUNK(v0, col0 + c * 16)
           if (c + 1 < nch) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (c + 2 < nch) TC_LD16(tbase + (uint32_t)(c + 2) * 16u, v0);
-            EPI_MIN(v1, col0 + (c + 1) * 16)
+            EPI_CHUNK(v1, col0 + (c + 1) * 16)
           }
         }
-#undef EPI_MIN
-        const float m = fminf(ma, mb);
-        const float thr = m + bound;
-        float acc = 0.f, accb = 0.f;
-#define EPI_HIT(V, COLBASE)                                                              \
-  {                                                                                      \
-    float p0 = 0.f, p1 = 0.f;                                                            \
-    _Pragma("unroll") for (int j4 = 0; j4 < 4; ++j4) {                                   \
-      const float d0 = __uint_as_float(V[j4 * 4 + 0]);                                   \
-      const float d1 = __uint_as_float(V[j4 * 4 + 1]);                                   \
-      const float d2 = __uint_as_float(V[j4 * 4 + 2]);                                   \
-      const float d3 = __uint_as_float(V[j4 * 4 + 3]);                                   \
-      p0 = fmaf(d0 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 0) * 0.0009765625f, p0);   \
-      p1 = fmaf(d1 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 1) * 0.0009765625f, p1);   \
-      p0 = fmaf(d2 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 2) * 0.0009765625f, p0);   \
-      p1 = fmaf(d3 <= thr ? 1.f : 0.f, 1.f + (float)(j4 * 4 + 3) * 0.0009765625f, p1);   \
-    }                                                                                    \
-    const float p = p0 + p1;                                                             \
-    acc += p;                                                                            \
-    accb += p >= 1.f ? (float)(COLBASE) : 0.f;                                           \
-  }
-        TC_LD16(tbase, v0);
-#pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c + 1 < nch) TC_LD16(tbase + (uint32_t)(c + 1) * 16u, v1);
-          EPI_HIT(v0, col0 + c * 16)
-          if (c + 1 < nch) {
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c + 2 < nch) TC_LD16(tbase + (uint32_t)(c + 2) * 16u, v0);
-            EPI_HIT(v1, col0 + (c + 1) * 16)
-          }
-        }
-#undef EPI_HIT
         tc_fence_before();
         mbar_arrive(BAR(BAR_ACC_EMPTY + set * NBUF + buf));
-        // acc < 2: one hit, (acc - 1) * 1024 = index inside its 16-column chunk, accb = that chunk's base
-        const float dec = acc < 2.f ? accb + (acc - 1.f) * 1024.f : -1.f;
-        if (u == 0) { um0 = m; ua0 = dec; } else { um1 = m; ua1 = dec; }
+        if (r == 0) TRACE(8 + 2 * u, it);
       }
-      // winner across units (unit 0 holds the lower indices: it wins exact ties)
-      const bool win1 = um1 < um0;
-      const float mw = win1 ? um1 : um0, mo = win1 ? um0 : um1, uaw = win1 ? ua1 : ua0;
+#undef EPI_CHUNK
+      const float thr = m1 + bound;
+      float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        p0 = fmaf(sv[i] <= thr ? 1.f : 0.f, 1.f + (float)i * 0.0009765625f, p0);
+        p1 = fmaf(sv[i + 1] <= thr ? 1.f : 0.f, 1.f + (float)(i + 1) * 0.0009765625f, p1);
+      }
+      const float hits = p0 + p1;
+      // hits < 2: one hit, (hits - 1) * 1024 = its index inside the saved chunk
+      const bool tie = !(hits >= 1.f && hits < 2.f) || !(m2 > thr) || out_of_range;
+      const int bj = tie ? 0 : (int)(sbase + (hits - 1.f) * 1024.f + 0.5f);
       const long long row = tile * BM + r;
       const bool valid = row < a.n;
-      const bool tie = uaw < 0.f || !(mo > mw + bound);
-      const int bj = tie ? 0 : (int)(uaw + 0.5f);
       const bool flagged = valid && tie && a.k > 1;
       if (valid && !flagged && a.labels) a.labels[row] = bj;
       if (flagged) {
@@ -521,17 +541,84 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         a.defer_idx[slot] = (int)row;
       }
       {
-        const int lb = (int)(it & 1);
-        mbar_wait(BAR(BAR_LAB_EMPTY + lb), (uint32_t)(((it >> 1) & 1) ^ 1));
-        lab_s[lb * BM + r] = (valid && !flagged) ? bj : -1;
-        mbar_arrive(BAR(BAR_LAB_FULL + lb));       // release semantics order the smem store
+        const int lb = (int)(it % NLAB);
+        mbar_wait(BAR(BAR_LAB_EMPTY + lb), (uint32_t)(((it / NLAB) & 1) ^ 1));
+        if (LANE_OWNS) {
+          // push the row onto its cluster's list (the owner lane of the M-step warps walks it)
+          int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
+          if (valid && !flagged) head[256 + r] = atomicExch(&head[bj], r);
+        } else {
+          lab_s[lb * BM + r] = (valid && !flagged) ? bj : -1;
+        }
+        mbar_arrive(BAR(BAR_LAB_FULL + lb));       // release semantics order the smem stores
+        if (r == 0) TRACE(11, it);
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 12 && LANE_OWNS) {
+    // =========================== M-step warps, lane-owns-cluster flavour ===========================
+    // Lane j of warp w owns cluster c = 32 w + j and keeps its d partial sums in registers.  The epilogue
+    // threads have linked the tile's rows into one list per cluster (head[c] -> next[row] -> ...); every lane
+    // walks its own list and adds whole rows (float4 reads of the swizzled tile: lanes with different
+    // row & 7 hit different banks).  No cross-lane traffic, no selection of an accumulator at run time,
+    // and 64 independent adds per row instead of a dependent chain per row.
+    const int wm = warp - 12;
+    const int c = wm * 32 + lane;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    int cnt = 0;
+    const bool two = KB > 1;
+#pragma unroll 1
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int lb = (int)(it % NLAB);
+      const int stage = (int)(it % NST);
+      mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it / NLAB) & 1));
+      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));   // completed long ago: acquire only
+      if (wm == 0 && lane == 0) TRACE(12, it);
+      int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
+      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+      int rr = head[c];
+      head[c] = -1;
+#pragma unroll 1
+      while (__any_sync(0xffffffffu, rr >= 0)) {
+        if (rr >= 0) {
+          const unsigned char* xr = xs + rr * 128;
+          const int sw = rr & 7;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(xr + ((q ^ sw) << 4));
+            acc[q * 4 + 0] += t.x; acc[q * 4 + 1] += t.y; acc[q * 4 + 2] += t.z; acc[q * 4 + 3] += t.w;
+          }
+          if (two) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(xr + KBLK_BYTES + ((q ^ sw) << 4));
+              acc[32 + q * 4 + 0] += t.x; acc[32 + q * 4 + 1] += t.y; acc[32 + q * 4 + 2] += t.z; acc[32 + q * 4 + 3] += t.w;
+            }
+          }
+          ++cnt;
+          rr = head[256 + rr];
+        }
+      }
+      __syncwarp();
+      if (wm == 0 && lane == 0) TRACE(13, it);
+      if (lane == 0) {
+        mbar_arrive(BAR(BAR_X_EMPTY + stage));
+        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+      }
+    }
+    if (lane == 0) red_s[wm] = 0.0;
+    if (c < a.k) {
+      float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d + (size_t)c * a.d;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) if (i < a.d) g[i] = acc[i];
+      a.pcnt[(size_t)blockIdx.x * a.k + c] = cnt;
+    }
+  } else if (warp >= 12 && !LANE_OWNS) {
     // =========================== distance + M-step warps ===========================
-    // Warp wm owns the rows whose label c satisfies c % 8 == wm.  Lane l holds features l and l+32 of
-    // the row (conflict-free reads of the swizzled tile): (a) the winning distance is re-evaluated
-    // exactly in fp32 direct form sum (x-c)^2 with c = -(bhi+blo)/2 read from the resident B tiles,
+    // Warp wm owns the rows whose label c satisfies c % NMW == wm.  Lane l holds features l and l+32 of
+    // the row (conflict-free reads of the swizzled tile): (a) [WANT_DIST] the winning distance is
+    // re-evaluated exactly in fp32 direct form sum (x-c)^2 against the fp32 centres in shared memory,
     // (b) [MSTEP] the row is added to the register-resident sums of cluster c.
     const int wm = warp - 12;
     float acc[256 / NMW][2];
@@ -540,20 +627,18 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     int cnt = 0;
     double inertia_acc = 0.0;
     const bool two = KB > 1;
-    mbar_wait(BAR(BAR_B_FULL), 0);
+    const float* c32 = reinterpret_cast<const float*>(smem + cfg.off_c32);
+    const int cpitch = KB * 32;
+    const uint32_t kstride = direct ? (uint32_t)KBLK_BYTES : (uint32_t)MKBLK_BYTES;   // bytes between K-blocks
 #define MSTEP_ROW(XA, XB, CC, ROWG)                                                               \
   {                                                                                               \
     const int c = (CC);                                                                           \
     const float x0 = (XA), x1 = (XB);                                                             \
     if (WANT_DIST) {                                                                              \
-      const uint32_t co = (uint32_t)(c * 128 + (((lane >> 2) ^ (c & 7)) << 4) + ((lane & 3) << 2)); \
-      float t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + co) +             \
-                           *reinterpret_cast<const float*>(smem + cfg.off_blo + co), x0);         \
+      float t = x0 - c32[c * cpitch + lane];                                                      \
       float s2 = t * t;                                                                           \
       if (two) {                                                                                  \
-        const uint32_t c1 = co + (uint32_t)NP * 128u;                                             \
-        t = fmaf(0.5f, *reinterpret_cast<const float*>(smem + cfg.off_bhi + c1) +                 \
-                       *reinterpret_cast<const float*>(smem + cfg.off_blo + c1), x1);             \
+        t = x1 - c32[c * cpitch + 32 + lane];                                                     \
         s2 = fmaf(t, t, s2);                                                                      \
       }                                                                                           \
       _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o); \
@@ -577,43 +662,52 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const int lb = (int)(it & 1);
+      const int lb = (int)(it % NLAB);
+      const int stage = (int)(it % NST);
+      // every warp polls on its own: a barrier across the 16 warps would make each step as slow as its
+      // most loaded warp
+      mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it / NLAB) & 1));
+      if (direct) mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));   // completed long ago: acquire only
+      if (wm == 0 && lane == 0) TRACE(12, it);
 #pragma unroll 1
       for (int h = 0; h < 4; ++h) {
         const long long mi = it * 4 + h;
         const int slot = (int)(mi & 1);
-        // every warp polls on its own: a per-quarter barrier across the 16 warps would make each quarter
-        // as slow as its most loaded warp
-        if (h == 0) mbar_wait(BAR(BAR_LAB_FULL + lb), (uint32_t)((it >> 1) & 1));
-        mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((mi >> 1) & 1));
-        const unsigned char* xs = smem + cfg.off_m + slot * (KB * MKBLK_BYTES);
-#pragma unroll 1
-        for (int base = 0; base < MH; base += 32) {
-          const int ml = lab_s[lb * BM + h * MH + base + lane];
-          unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & (NMW - 1)) == wm);
-#pragma unroll 1
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int cq = __shfl_sync(0xffffffffu, ml, b) & 255;
-            const int rh = base + b;      // row inside the 64-row half tile
-            const uint32_t ro = (uint32_t)(rh * 128 + (((lane >> 2) ^ (rh & 7)) << 4) + ((lane & 3) << 2));
-            const float xa = *reinterpret_cast<const float*>(xs + ro);
-            const float xb = two ? *reinterpret_cast<const float*>(xs + MKBLK_BYTES + ro) : 0.f;
-            MSTEP_ROW(xa, xb, cq, tile * BM + h * MH + base + b)
-          }
+        const unsigned char* xs;
+        if (direct) {
+          xs = smem + cfg.off_x + stage * stage_bytes + h * MKBLK_BYTES;
+        } else {
+          mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((mi >> 1) & 1));
+          xs = smem + cfg.off_m + slot * (KB * MKBLK_BYTES);
         }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(BAR(BAR_M_EMPTY + slot));
-          if (h == 3) mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+        const int ml = lab_s[lb * BM + h * MH + lane];
+        unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml & (NMW - 1)) == wm);
+#pragma unroll 1
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int cq = __shfl_sync(0xffffffffu, ml, b) & 255;
+          const uint32_t ro = (uint32_t)(b * 128 + (((lane >> 2) ^ (b & 7)) << 4) + ((lane & 3) << 2));
+          const float xa = *reinterpret_cast<const float*>(xs + ro);
+          const float xb = two ? *reinterpret_cast<const float*>(xs + kstride + ro) : 0.f;
+          MSTEP_ROW(xa, xb, cq, tile * BM + h * MH + b)
         }
+        if (!direct) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(BAR_M_EMPTY + slot));
+        }
+      }
+      __syncwarp();
+      if (wm == 0 && lane == 0) TRACE(13, it);
+      if (lane == 0) {
+        if (direct) mbar_arrive(BAR(BAR_X_EMPTY + stage));
+        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
       }
     }
 #undef MSTEP_ROW
     if (lane == 0) red_s[wm] = inertia_acc;
     if (MSTEP) {
-      // flush the register-resident sums: cluster c = wm + 8 j, features lane and lane + 32
+      // flush the register-resident sums: cluster c = wm + NMW j, features lane and lane + 32
       float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d;
 #pragma unroll
       for (int j = 0; j < 256 / NMW; ++j) {
@@ -633,8 +727,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    double t = red_s[NMW];
-    for (int w = 0; w < NMW; ++w) t += red_s[w];
+    double t = red_s[NMWK];
+    for (int w = 0; w < NMWK; ++w) t += red_s[w];
     a.pin[blockIdx.x] = t;
   }
   if (warp == 2) {
@@ -731,15 +825,18 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows][cols] with row pitch `pitch_elems`, box = 32 columns x box_rows, 128B swizzle
-static int make_map(CUtensorMap* tm, const void* base, long long rows, int cols, long long pitch_elems, int box_rows) {
+// 2-D tensor [rows][cols] (fp32, or fp16 when half16) with row pitch `pitch_elems`; box = one 128-byte
+// swizzle atom of columns (32 fp32 / 64 fp16) x box_rows
+static int make_map(CUtensorMap* tm, const void* base, long long rows, int cols, long long pitch_elems, int box_rows,
+                    bool half16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return BKM_EUNSUPPORTED;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * (half16 ? 2 : 4)};
+  cuuint32_t box[2] = {half16 ? 64u : 32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(tm, half16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : BKM_EUNSUPPORTED;
@@ -750,66 +847,80 @@ unsigned int tc_abort_code() {
   cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(v));
   return v;
 }
+int tc_trace(long long* out, int n) {
+#if BKM_TRACE
+  if (n > 16 * 128) n = 16 * 128;
+  cudaMemcpyFromSymbol(out, g_tc_trace, (size_t)n * sizeof(long long));
+  return n;
+#else
+  (void)out; (void)n;
+  return 0;
+#endif
+}
 void tc_abort_detail(unsigned int* out64) { cudaMemcpyFromSymbol(out64, g_tc_dbg, 64 * sizeof(unsigned int)); }
 
 bool tc_supported(int d, int k, int dtype) {
   return dtype == BKM_F32 && d >= 4 && d <= 64 && (d % 4) == 0 && k >= 1 && k <= 256;
 }
 
-static bool make_cfg(int d, int k, TcCfg* c) {
+static bool make_cfg(int d, int k, bool want_dist, TcCfg* c) {
   c->KB = (d + 31) / 32;
-  c->KS = (d + 7) / 8;
+  c->KS = (d + 15) / 16;
   c->NP = (k + 15) / 16 * 16;
   if (c->NP <= 128) { c->NU0 = c->NP; c->NU1 = 0; c->U = 1; }
   else { c->NU0 = (c->NP / 2 + 15) / 16 * 16; c->NU1 = c->NP - c->NU0; c->U = c->NU1 > 0 ? 2 : 1; }
-  const uint32_t bbytes = (uint32_t)c->KB * c->NP * 128u;
-  for (int nst = 3; nst >= 2; --nst) {
-    uint32_t o = 0;
-    c->off_bhi = o; o += bbytes;
-    c->off_blo = o; o += bbytes;
-    o = (uint32_t)align_up(o, 1024);
-    c->off_bcn = o; o += (uint32_t)c->NP * 32u;                  // ||c||^2 operand tile
-    c->off_ones = o; o += BM * 32u;                              // constant [1,1,1,0..] A tile
-    o = (uint32_t)align_up(o, 1024);
-    c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring (MMA + Xlo converter)
-    c->off_m = o; o += 2u * c->KB * MKBLK_BYTES;                 // M ring (M-step / distance warps)
-    c->off_cn = o;
-    c->off_lab = o; o += 2 * BM * 4;
-    c->off_flist = o;
-    c->off_red = o; o += (NMW + 1) * 8;
-    c->off_bar = o; o += BAR_COUNT * 8;
-    c->off_tptr = o; o += 16;
-    c->total = o;
-    c->NST = nst;
-    if (o <= 227 * 1024) return true;
+  const uint32_t bbytes = (uint32_t)c->NP * 128u;               // one fp16 B tile: NP rows x 64 halves
+  // direct mode (the M-step warps read the A ring) needs a ring deep enough to cover load -> convert -> MMA ->
+  // epilogue -> M-step; otherwise 2-3 stages plus the separate M ring.
+  for (int direct = 1; direct >= 0; --direct) {
+    for (int nst = direct ? NSTMAX : 3; nst >= (direct ? 4 : 2); --nst) {
+      uint32_t o = 0;
+      c->off_bhi = o; o += bbytes;
+      c->off_blo = o; o += bbytes;
+      c->off_bcn = o; o += (uint32_t)c->NP * 32u;                  // ||c||^2 operand tile
+      c->off_ones = o; o += BM * 32u;                              // constant [1,1,1,0..] A tile
+      c->off_c32 = o; if (want_dist) o += (uint32_t)c->NP * c->KB * 128u;   // fp32 centres (distance variants)
+      o = (uint32_t)align_up(o, 1024);
+      c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring
+      c->off_m = o; if (!direct) o += 2u * c->KB * MKBLK_BYTES;    // M ring
+      c->off_lab = o; o += NLAB * LIST_BYTES;                      // label buffers / per-cluster row lists
+      c->off_red = o; o += (NMW + 1) * 8;
+      c->off_bar = o; o += BAR_COUNT * 8;
+      c->off_tptr = o; o += 16;
+      c->total = o;
+      c->NST = nst;
+      c->direct = direct;
+      if (o <= 227 * 1024) return true;
+    }
   }
   return false;
 }
 
 int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
+  const bool want_dist = !mstep || a.min_out != nullptr || a.want_sum;
   TcCfg cfg;
-  if (!make_cfg(a.d, a.k, &cfg)) return BKM_EUNSUPPORTED;
+  if (!make_cfg(a.d, a.k, want_dist, &cfg)) return BKM_EUNSUPPORTED;
+  if (mstep && !want_dist && !cfg.direct) return BKM_EUNSUPPORTED;      // the lane-owns-cluster M-step reads the A ring
   CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
   int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
   if (rc) return rc;
   rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, MH);
   if (rc) return rc;
-  rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
+  rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dh, a.L.dh, cfg.NP, true);
   if (rc) return rc;
-  rc = make_map(&tm_blo, a.pack + a.L.off_blo, a.L.kp, a.L.dk, a.L.dk, cfg.NP);
+  rc = make_map(&tm_blo, a.pack + a.L.off_blo, a.L.kp, a.L.dh, a.L.dh, cfg.NP, true);
   if (rc) return rc;
   long long ntiles = (a.n + BM - 1) / BM;
   int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
   if (grid < 1) grid = 1;
   *grid_out = grid;
-  const bool want_dist = !mstep || a.min_out != nullptr || a.want_sum;
   BKM_CUDA_TRY(cudaMemsetAsync(a.defer_cnt, 0, sizeof(int), s));
 #define TC_LAUNCH(M, W)                                                                                       \
   {                                                                                                           \
     BKM_CUDA_TRY(cudaFuncSetAttribute(tc_chunk_kernel<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                       (int)cfg.total));                                                       \
-    tc_chunk_kernel<M, W><<<grid, TC_THREADS, cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);                  \
+    tc_chunk_kernel<M, W><<<grid, tc_threads(M, W), cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);                  \
   }
   if (mstep) { if (want_dist) TC_LAUNCH(true, true) else TC_LAUNCH(true, false) }
   else TC_LAUNCH(false, true)

@@ -140,6 +140,8 @@ int64_t bkm_launch_count(void);
  * instead of hanging); encodes barrier / parity / warp.  Synchronises the device. */
 unsigned int bkm_debug_abort_code(void);
 void bkm_debug_abort_detail(unsigned int* out64_host);   /* per-warp wait that timed out (64 words) */
+/* `make TRACE=1` builds only: SM-clock timeline of CTA 0 (16 events x 128 tiles); returns words written, 0 otherwise */
+int bkm_debug_trace(long long* out_host, int n);
 
 #ifdef __cplusplus
 }
