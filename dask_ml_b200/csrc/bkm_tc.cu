@@ -33,11 +33,17 @@
 namespace bkm {
 
 static const int BM = 128;           // rows per tile
+// Roles are assigned per aligned group of 4 warps (setmaxnreg moves registers between whole warpgroups):
+// warps 0-3: TMA producer (0), MMA issuer (1), 2 spare; 4-7 converter; 8-11 / 12-15 epilogue sets; 16+ M-step
+static const int MW0 = 16;
 static const int NMW = 16;               // distance variants: 16 distance + M-step warps (warp owns the clusters c % 16)
 static const int NMW_LANE = 8;           // pure Lloyd variant: 8 M-step warps, LANE j of warp w owns cluster 32 w + j
 static const int LIST_BYTES = 256 * 4 + BM * 4;   // per label buffer: head[256] + next[128] (row lists per cluster)
 __host__ __device__ constexpr int tc_mwarps(bool mstep, bool want_dist) { return (mstep && !want_dist) ? NMW_LANE : NMW; }
-__host__ __device__ constexpr int tc_threads(bool mstep, bool want_dist) { return (12 + tc_mwarps(mstep, want_dist)) * 32; }
+// register cap: registers are allocated per warp in units of 512 (16 per thread)
+// (each of the 4 SM sub-partitions holds 16384 registers and ceil(warps / 4) of the CTA's warps)
+__host__ __device__ constexpr int tc_maxreg(bool mstep, bool want_dist) { return 16384 / ((MW0 + tc_mwarps(mstep, want_dist) + 3) / 4) / 512 * 16; }
+__host__ __device__ constexpr int tc_threads(bool mstep, bool want_dist) { return (MW0 + tc_mwarps(mstep, want_dist)) * 32; }
 static const int KBLK_BYTES = BM * 128;   // one K-block (32 fp32 columns) of a 128-row tile
 static const int MH = 32;                 // rows per M-ring stage (a quarter tile)
 static const int MKBLK_BYTES = MH * 128;
@@ -50,7 +56,8 @@ struct TcCfg {
   int U;
   int NST;       // X stages
   int direct;    // 1: the M-step warps read the A ring; 0: separate M ring
-  uint32_t off_bhi, off_blo, off_bcn, off_ones, off_c32, off_x, off_m, off_lab, off_red, off_bar, off_tptr, total;
+  int MR;        // rows per M-ring slot (32: quarter tiles, 128: whole tiles)
+  uint32_t off_bhi, off_blo, off_bcn, off_ones, off_c32, off_x, off_m, off_lab, off_xn, off_red, off_bar, off_tptr, total;
 };
 
 static const int NBUF = 3;               // 128-column TMEM accumulator buffers (3*128 acc + 2*(32 Xhi + 32 Xlo) = 512)
@@ -64,8 +71,10 @@ enum {
   BAR_X_EMPTY = BAR_X_FULL + NSTMAX,       // [NSTMAX]
   BAR_ACC_FULL = BAR_X_EMPTY + NSTMAX,     // [set 2][buf 3]  one barrier per (epilogue warp set, accumulator buffer): every
   BAR_ACC_EMPTY = BAR_ACC_FULL + 6,        // [set 2][buf 3]  waiter then observes consecutive phases (no parity aliasing)
-  BAR_XOP_FULL = BAR_ACC_EMPTY + 6,        // [2]   X operands of tile (it & 1) are in TMEM
-  BAR_LAB_FULL = BAR_XOP_FULL + 2,         // [NLAB]
+  BAR_XOP_FULL = BAR_ACC_EMPTY + 6,        // [4]   X operands (and ||x||^2) of tile it are ready; indexed it & 3 so that
+                                           //       the epilogue's late acquire cannot alias a newer phase
+  BAR_XOP_EMPTY = BAR_XOP_FULL + 4,        // [2]   ... and the MMAs that read them have completed
+  BAR_LAB_FULL = BAR_XOP_EMPTY + 2,        // [NLAB]
   BAR_LAB_EMPTY = BAR_LAB_FULL + NLAB,     // [NLAB]
   BAR_M_FULL = BAR_LAB_EMPTY + NLAB,       // [2]  M ring (ring mode): 32-row quarter tiles re-fetched (L2 hits)
   BAR_M_EMPTY = BAR_M_FULL + 2,            // [2]
@@ -122,6 +131,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       return;
     }
   }
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
 }
 // Long waits (a whole pipeline stage away): poll with back-off so that the poller does not steal
 // issue slots from the warps doing the work on the same SM sub-partition.
@@ -263,6 +281,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       mbar_init(BAR(BAR_M_FULL + b), 1);
       mbar_init(BAR(BAR_M_EMPTY + b), NMWK);
       mbar_init(BAR(BAR_XOP_FULL + b), 128);
+      mbar_init(BAR(BAR_XOP_FULL + 2 + b), 128);
+      mbar_init(BAR(BAR_XOP_EMPTY + b), (uint32_t)U);
     }
     for (int b = 0; b < NLAB; ++b) {
       mbar_init(BAR(BAR_LAB_FULL + b), 128);
@@ -271,7 +291,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     red_s[NMWK] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tptr_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -307,53 +327,81 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   tc_fence_after();
   const uint32_t tmem = *tptr_s;
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+  // Register re-allocation between warpgroups (pure Lloyd variant, launched with 80 registers per thread): the
+  // producer / MMA group and the converter give registers up, the M-step warps (64 running sums per lane plus
+  // several 16-byte loads in flight) take them.  Per SM sub-partition: 40+72+80+80+104+104 = 6*80.  The
+  // instruction sits at the top of every role's branch so that the compiler sees one budget per branch.
+#define REG_DEC(n) do { if (LANE_OWNS) asm volatile("setmaxnreg.dec.sync.aligned.u32 " #n ";"); } while (0)
+#define REG_INC(n) do { if (LANE_OWNS) asm volatile("setmaxnreg.inc.sync.aligned.u32 " #n ";"); } while (0)
+
+  if (warp == 0 || warp == 3) {
+    REG_DEC(40);
+    // =========================== TMA producer (warp 0; warp 3 is spare) ===========================
+    // One thread feeds both rings from a polling loop (neither ring may block the other).  A ring: 128-row X
+    // tiles, with an L2 prefetch PF tiles ahead.  M ring (ring mode only): every tile is re-fetched as four
+    // 32-row quarters for the M-step / distance warps; the same rows were loaded for the converter a few
+    // microseconds earlier, so these are L2 hits and HBM traffic stays at one read of X per iteration.
+    if (warp == 0 && lane == 0) {
       mbar_expect_tx(BAR(BAR_B_FULL), 2u * (uint32_t)NP * 128u);
       tma_load_2d(s_bhi, &tm_bhi, BAR(BAR_B_FULL), 0, 0);
       tma_load_2d(s_blo, &tm_blo, BAR(BAR_B_FULL), 0, 0);
       const int PF = 6;        // L2 prefetch distance (tiles) ahead of the shared-memory ring
       for (long long it = 0; it < PF && it < my_tiles; ++it)
         for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((blockIdx.x + it * gridDim.x) * BM));
-#pragma unroll 1
-      for (long long it = 0; it < my_tiles; ++it) {
-        const long long tile = blockIdx.x + it * gridDim.x;
-        const int stage = (int)(it % NST);
-        const uint32_t ph = (uint32_t)((it / NST) & 1);
-        if (it + PF < my_tiles)
-          for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((tile + (long long)PF * gridDim.x) * BM));
-        mbar_wait(BAR(BAR_X_EMPTY + stage), ph ^ 1u);
-        TRACE(0, it);
-        mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
-                      kb * 32, (int)(tile * BM));
-      }
-    }
-  } else if (warp == 3) {
-    // =========================== TMA producer of the M ring (ring mode) ===========================
-    // Re-fetches every tile as four 32-row quarters for the M-step / distance warps.  The same rows were
-    // loaded for the MMA a few microseconds earlier, so these are L2 hits: HBM traffic stays at one read
-    // of X per iteration while the M-step does not hold the (short) A ring.
-    if (lane == 0 && !direct) {
       const uint32_t s_m = sbase + cfg.off_m;
-      const uint32_t mbytes = (uint32_t)KB * MKBLK_BYTES;
+      const int MR = cfg.MR;                              // rows per M-ring slot: 32 (quarter tiles) or 128
+      const int qpt = BM / MR;                            // slots per tile
+      const uint32_t mkblk = (uint32_t)MR * 128u;
+      const uint32_t mbytes = (uint32_t)KB * mkblk;
+      const long long m_total = direct ? 0 : qpt * my_tiles;
+      long long ait = 0, mi = 0;
+      uint32_t idle = 0;
 #pragma unroll 1
-      for (long long mi = 0; mi < 4 * my_tiles; ++mi) {
-        const long long tile = blockIdx.x + (mi >> 2) * gridDim.x;
-        const int slot = (int)(mi & 1);
-        mbar_wait(BAR(BAR_M_EMPTY + slot), (uint32_t)(((mi >> 1) & 1) ^ 1));
-        mbar_expect_tx(BAR(BAR_M_FULL + slot), mbytes);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(s_m + slot * mbytes + (uint32_t)kb * MKBLK_BYTES, &tm_xm, BAR(BAR_M_FULL + slot), kb * 32,
-                      (int)(tile * BM + (mi & 3) * MH));
+      while (ait < my_tiles || mi < m_total) {
+        bool progressed = false;
+        if (ait < my_tiles) {
+          const int stage = (int)(ait % NST);
+          if (mbar_test(BAR(BAR_X_EMPTY + stage), (uint32_t)(((ait / NST) & 1) ^ 1))) {
+            const long long tile = blockIdx.x + ait * gridDim.x;
+            TRACE(0, ait);
+            if (ait + PF < my_tiles)
+              for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((tile + (long long)PF * gridDim.x) * BM));
+            mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
+                          kb * 32, (int)(tile * BM));
+            ++ait;
+            progressed = true;
+          }
+        }
+        if (mi < m_total && (mi / qpt) < ait) {
+          const int slot = (int)(mi & 1);
+          if (mbar_test(BAR(BAR_M_EMPTY + slot), (uint32_t)(((mi >> 1) & 1) ^ 1))) {
+            const long long tile = blockIdx.x + (mi / qpt) * gridDim.x;
+            mbar_expect_tx(BAR(BAR_M_FULL + slot), mbytes);
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_2d(s_m + slot * mbytes + (uint32_t)kb * mkblk, &tm_xm, BAR(BAR_M_FULL + slot), kb * 32,
+                          (int)(tile * BM + (mi % qpt) * MR));
+            ++mi;
+            progressed = true;
+          }
+        }
+        if (progressed) { idle = 0; continue; }
+        __nanosleep(64);
+        if (++idle > (1u << 22) || ((idle & 255) == 255 && *(volatile unsigned int*)&g_tc_abort)) {
+          atomicCAS(&g_tc_abort, 0u, 0x80000000u | (0xfffu << 12));
+          break;
+        }
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    // The whole warp runs this loop converged (all addresses / descriptors are warp-uniform and live
-    // in uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
+  } else if (warp == 1 || warp == 2) {
+    REG_DEC(40);
+    // =========================== MMA issuers ===========================
+    // Two dedicated warps take alternate accumulator units (unit g = tile * U + u goes to warp 1 + (g & 1)):
+    // the thread that issues tcgen05.mma stalls on its next instructions until the tensor core has accepted
+    // the queued MMAs, so a single issuer leaves the tensor pipe idle between units.  Each warp runs its loop
+    // converged (all addresses / descriptors are warp-uniform and live in uniform registers); only the
+    // tcgen05 instructions themselves are issued by one elected lane.
     const bool leader = elect_one();      // one lane issues every tcgen05.mma / commit (same thread: ordered)
     mbar_wait(BAR(BAR_B_FULL), 0);
     tc_fence_after();
@@ -362,106 +410,120 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     const uint64_t dns = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint64_t dcn = dns | (uint64_t)(((sbase + cfg.off_bcn) >> 4) & 0x3FFF);
     const uint64_t dones = dns | (uint64_t)(((sbase + cfg.off_ones) >> 4) & 0x3FFF);
+    const long long g_total = my_tiles * U;
 #pragma unroll 1
-    for (long long it = 0; it < my_tiles; ++it) {
+    for (long long g = warp - 1; g < g_total; g += 2) {
+      const long long it = U == 2 ? (g >> 1) : g;
+      const int u = U == 2 ? (int)(g & 1) : 0;
       // Both X operands live in TMEM (fp16 pairs written by the converter): only the 4 KB B slice of each
       // K-step is fetched from shared memory.
       const uint32_t xhi_t = tmem + TM_XHI + (uint32_t)(it & 1) * 32u;
       const uint32_t xlo_t = tmem + TM_XLO + (uint32_t)(it & 1) * 32u;
-#pragma unroll 1
-      for (int u = 0; u < U; ++u) {
-        const long long g = it * U + u;
-        const int buf = (int)(g % NBUF);
-        if (g >= NBUF) {
-          // the buffer was last used by unit g-NBUF, consumed by epilogue set ((g-NBUF)/U) & 1
-          const long long gp = g - NBUF;
-          mbar_wait(BAR(BAR_ACC_EMPTY + (int)((gp / U) & 1) * NBUF + buf), acc_parity(gp, U));
-        }
-        if (u == 0) mbar_wait(BAR(BAR_XOP_FULL + (it & 1)), (uint32_t)((it >> 1) & 1));
-        tc_fence_after();
-        if (leader) TRACE(3 + 2 * u, it);
-        const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
-        const uint32_t rowoff = u == 0 ? 0u : (uint32_t)cfg.NU0 * 128u;
-        const uint32_t idesc = make_idesc_f16(ncols);
-        const uint32_t d_t = tmem + (uint32_t)buf * 128u;
-        const uint64_t dbh = dflags | (uint64_t)(((s_bhi + rowoff) >> 4) & 0x3FFF);
-        const uint64_t dbl = dflags | (uint64_t)(((s_blo + rowoff) >> 4) & 0x3FFF);
-        if (leader) {
-          // Xhi . Bhi   (K-step s: 16 halves = 32 bytes inside the 128-byte swizzle atom, 8 TMEM columns)
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, s > 0 ? 1u : 0u);
-          // Xhi . Blo
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbl + (uint64_t)(s * 2), idesc, 1u);
-          // Xlo . Bhi
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < KS) mma_f16_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, 1u);
-          mma_tf32_ss(d_t, dones, dcn + (uint64_t)(rowoff >> 6), make_idesc_tf32(ncols), 1u);     // + s^2 ||c_j||^2
-          tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * NBUF + buf));
-          TRACE(4 + 2 * u, it);
-        }
-        __syncwarp();
+      const int buf = (int)(g % NBUF);
+      if (g >= NBUF) {
+        // the buffer was last used by unit g-NBUF, consumed by epilogue set ((g-NBUF)/U) & 1
+        const long long gp = g - NBUF;
+        mbar_wait(BAR(BAR_ACC_EMPTY + (int)((gp / U) & 1) * NBUF + buf), acc_parity(gp, U));
       }
+      mbar_wait(BAR(BAR_XOP_FULL + (it & 3)), (uint32_t)((it >> 2) & 1));
+      tc_fence_after();
+      if (leader) TRACE(3 + 2 * u, it);
+      const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
+      const uint32_t rowoff = u == 0 ? 0u : (uint32_t)cfg.NU0 * 128u;
+      const uint32_t idesc = make_idesc_f16(ncols);
+      const uint32_t d_t = tmem + (uint32_t)buf * 128u;
+      const uint64_t dbh = dflags | (uint64_t)(((s_bhi + rowoff) >> 4) & 0x3FFF);
+      const uint64_t dbl = dflags | (uint64_t)(((s_blo + rowoff) >> 4) & 0x3FFF);
+      if (leader) {
+        // Xhi . Bhi   (K-step s: 16 halves = 32 bytes inside the 128-byte swizzle atom, 8 TMEM columns)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, s > 0 ? 1u : 0u);
+        // Xhi . Blo
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbl + (uint64_t)(s * 2), idesc, 1u);
+        // Xlo . Bhi
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (s < KS) mma_f16_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, 1u);
+        mma_tf32_ss(d_t, dones, dcn + (uint64_t)(rowoff >> 6), make_idesc_tf32(ncols), 1u);     // + s^2 ||c_j||^2
+        tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * NBUF + buf));
+        tc_commit(BAR(BAR_XOP_EMPTY + (it & 1)));      // one arrival per unit: the tile's X operands are free after U of them
+        TRACE(4 + 2 * u, it);
+      }
+      __syncwarp();
     }
-  } else if (warp >= 4 && warp < 12) {
-    // =========================== X converter + epilogue ===========================
-    // Two warp sets (warps 4-7 and 8-11) take alternate tiles, so each SM sub-partition has two epilogue
-    // warps whose instruction streams interleave.  Thread == row == TMEM lane.
-    const int set = (warp - 4) >> 2;
+  } else if (warp >= 4 && warp < 8) {
+    REG_DEC(72);
+    // =========================== X converter ===========================
+    // Thread == row == TMEM lane (warp & 3 selects the lane quarter).  Runs ahead of the MMA: tile it + 2 is
+    // converted as soon as the MMAs of tile it have released the TMEM operand slot.
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const float sc = reinterpret_cast<const PackHeader*>(a.pack)->scale;
+    float* xn_s = reinterpret_cast<float*>(smem + cfg.off_xn);       // [4][BM]
+    uint32_t xoff[8];                              // swizzled 16-byte chunk offsets of this thread's row
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
+#pragma unroll 1
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int stage = (int)(it % NST);
+      // ---- s X -> fp16 (hi, lo) pairs in TMEM, and ||s x||^2 ----
+      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+      mbar_wait(BAR(BAR_XOP_EMPTY + (it & 1)), (uint32_t)(((it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      if (r == 0) TRACE(1, it);
+      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+      float xn4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        uint32_t v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + xoff[q]);
+          v[q * 4 + 0] = __float_as_uint(t.x); v[q * 4 + 1] = __float_as_uint(t.y);
+          v[q * 4 + 2] = __float_as_uint(t.z); v[q * 4 + 3] = __float_as_uint(t.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float e0 = __uint_as_float(v[2 * j]) * sc, e1 = __uint_as_float(v[2 * j + 1]) * sc;
+          xn4[j & 3] = fmaf(e0, e0, xn4[j & 3]);
+          xn4[(j + 2) & 3] = fmaf(e1, e1, xn4[(j + 2) & 3]);
+          const __half2 h = __floats2half2_rn(e0, e1);          // low half = K element 2j
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);      // the subtraction is exact
+          v[2 * j] = *reinterpret_cast<const uint32_t*>(&h);
+          v[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        TC_ST16S(tmem + lane_addr + TM_XHI + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 0);
+        TC_ST16S(tmem + lane_addr + TM_XLO + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 1);
+      }
+      xn_s[(it & 3) * BM + r] = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
+      mbar_arrive(BAR(BAR_X_EMPTY + stage));        // the converter is done with the smem stage
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(BAR(BAR_XOP_FULL + (it & 3)));      // release: also publishes xn_s
+      if (r == 0) TRACE(2, it);
+    }
+  } else if (warp >= 8 && warp < MW0) {
+    // =========================== epilogue ===========================
+    // Two warp sets (warps 8-11 and 12-15) take alternate tiles, so each SM sub-partition has two epilogue
+    // warps whose TMEM loads and instruction streams interleave.  Thread == row == TMEM lane.
+    const int set = (warp - 8) >> 2;
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     const PackHeader* hdr = reinterpret_cast<const PackHeader*>(a.pack);
-    const float sc = hdr->scale;
-    const float cnmax = (float)(hdr->cn_max * (double)sc * (double)sc);
-    uint32_t xoff[8];                              // swizzled 16-byte chunk offsets of this thread's row
-#pragma unroll
-    for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
-    mbar_wait(BAR(BAR_B_FULL), 0);
+    const float cnmax = (float)(hdr->cn_max * (double)hdr->scale * (double)hdr->scale);
+    const float* xn_s = reinterpret_cast<const float*>(smem + cfg.off_xn);
 #pragma unroll 1
     for (long long it = set; it < my_tiles; it += 2) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const int stage = (int)(it % NST);
-      // ---- convert: s X -> fp16 (hi, lo) pairs in TMEM, and ||s x||^2 ----
-      float xn;
-      {
-        mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
-        if (r == 0) TRACE(1, it);
-        const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
-        float xn4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          uint32_t v[32];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(xs + kb * KBLK_BYTES + xoff[q]);
-            v[q * 4 + 0] = __float_as_uint(t.x); v[q * 4 + 1] = __float_as_uint(t.y);
-            v[q * 4 + 2] = __float_as_uint(t.z); v[q * 4 + 3] = __float_as_uint(t.w);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = __uint_as_float(v[2 * j]) * sc, e1 = __uint_as_float(v[2 * j + 1]) * sc;
-            xn4[j & 3] = fmaf(e0, e0, xn4[j & 3]);
-            xn4[(j + 2) & 3] = fmaf(e1, e1, xn4[(j + 2) & 3]);
-            const __half2 h = __floats2half2_rn(e0, e1);          // low half = K element 2j
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);      // the subtraction is exact
-            v[2 * j] = *reinterpret_cast<const uint32_t*>(&h);
-            v[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l);
-          }
-          TC_ST16S(tmem + lane_addr + TM_XHI + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 0);
-          TC_ST16S(tmem + lane_addr + TM_XLO + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 1);
-        }
-        xn = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
-        mbar_arrive(BAR(BAR_X_EMPTY + stage));        // this set is done with the smem stage
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(BAR(BAR_XOP_FULL + (it & 1)));
-        if (r == 0) TRACE(2, it);
-      }
+      // the converter published ||s x||^2 before it released the operands (completed long ago: acquire only)
+      mbar_wait(BAR(BAR_XOP_FULL + (it & 3)), (uint32_t)((it >> 2) & 1));
+      const float xn = xn_s[(it & 3) * BM + r];
       const float bound = a.tau * (xn + cnmax);
       // an entry beyond fp16's range (|s x| >= 65504 => xn >= 4.29e9) or a non-finite one: float64 path
       const bool out_of_range = !(xn < 4.29e9f);
@@ -554,14 +616,17 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         if (r == 0) TRACE(11, it);
       }
     }
-  } else if (warp >= 12 && LANE_OWNS) {
+  } else if (warp >= MW0 && LANE_OWNS) {
+    REG_INC(104);
     // =========================== M-step warps, lane-owns-cluster flavour ===========================
-    // Lane j of warp w owns cluster c = 32 w + j and keeps its d partial sums in registers.  The epilogue
+    // Lane j of warp w owns cluster c = 32 w + j and keeps its d partial sums in registers.  The rows come
+    // from the M ring (two full-tile slots, re-fetched from L2 while the tile's epilogue runs), so the A ring
+    // only has to cover load -> convert and two stages are enough.  The epilogue
     // threads have linked the tile's rows into one list per cluster (head[c] -> next[row] -> ...); every lane
     // walks its own list and adds whole rows (float4 reads of the swizzled tile: lanes with different
     // row & 7 hit different banks).  No cross-lane traffic, no selection of an accumulator at run time,
     // and 64 independent adds per row instead of a dependent chain per row.
-    const int wm = warp - 12;
+    const int wm = warp - MW0;
     const int c = wm * 32 + lane;
     float acc[64];
 #pragma unroll
@@ -571,16 +636,22 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
       const int lb = (int)(it % NLAB);
-      const int stage = (int)(it % NST);
+      const int slot = (int)(it & 1);
       mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it / NLAB) & 1));
-      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));   // completed long ago: acquire only
+      mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((it >> 1) & 1));
       if (wm == 0 && lane == 0) TRACE(12, it);
       int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
-      const unsigned char* xs = smem + cfg.off_x + stage * stage_bytes;
+      const unsigned char* xs = smem + cfg.off_m + slot * stage_bytes;      // full-tile slot: same layout as an A stage
       int rr = head[c];
       head[c] = -1;
+#if BKM_TRACE
+      int witers = 0;
+#endif
 #pragma unroll 1
       while (__any_sync(0xffffffffu, rr >= 0)) {
+#if BKM_TRACE
+        ++witers;
+#endif
         if (rr >= 0) {
           const unsigned char* xr = xs + rr * 128;
           const int sw = rr & 7;
@@ -602,8 +673,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       }
       __syncwarp();
       if (wm == 0 && lane == 0) TRACE(13, it);
+#if BKM_TRACE
+      if (wm == 0 && lane == 0 && blockIdx.x == 0 && it < 128) g_tc_trace[14 * 128 + (int)it] = witers;
+#endif
       if (lane == 0) {
-        mbar_arrive(BAR(BAR_X_EMPTY + stage));
+        mbar_arrive(BAR(BAR_M_EMPTY + slot));
         mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
       }
     }
@@ -614,13 +688,13 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       for (int i = 0; i < 64; ++i) if (i < a.d) g[i] = acc[i];
       a.pcnt[(size_t)blockIdx.x * a.k + c] = cnt;
     }
-  } else if (warp >= 12 && !LANE_OWNS) {
+  } else if (warp >= MW0 && !LANE_OWNS) {
     // =========================== distance + M-step warps ===========================
     // Warp wm owns the rows whose label c satisfies c % NMW == wm.  Lane l holds features l and l+32 of
     // the row (conflict-free reads of the swizzled tile): (a) [WANT_DIST] the winning distance is
     // re-evaluated exactly in fp32 direct form sum (x-c)^2 against the fp32 centres in shared memory,
     // (b) [MSTEP] the row is added to the register-resident sums of cluster c.
-    const int wm = warp - 12;
+    const int wm = warp - MW0;
     float acc[256 / NMW][2];
 #pragma unroll
     for (int j = 0; j < 256 / NMW; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
@@ -731,7 +805,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     for (int w = 0; w < NMWK; ++w) t += red_s[w];
     a.pin[blockIdx.x] = t;
   }
-  if (warp == 2) {
+  if (warp == 0) {
+    __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
 #undef BAR
@@ -863,17 +938,20 @@ bool tc_supported(int d, int k, int dtype) {
   return dtype == BKM_F32 && d >= 4 && d <= 64 && (d % 4) == 0 && k >= 1 && k <= 256;
 }
 
-static bool make_cfg(int d, int k, bool want_dist, TcCfg* c) {
+static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {
+  const bool lane_owns = mstep && !want_dist;
   c->KB = (d + 31) / 32;
   c->KS = (d + 15) / 16;
   c->NP = (k + 15) / 16 * 16;
   if (c->NP <= 128) { c->NU0 = c->NP; c->NU1 = 0; c->U = 1; }
   else { c->NU0 = (c->NP / 2 + 15) / 16 * 16; c->NU1 = c->NP - c->NU0; c->U = c->NU1 > 0 ? 2 : 1; }
   const uint32_t bbytes = (uint32_t)c->NP * 128u;               // one fp16 B tile: NP rows x 64 halves
-  // direct mode (the M-step warps read the A ring) needs a ring deep enough to cover load -> convert -> MMA ->
-  // epilogue -> M-step; otherwise 2-3 stages plus the separate M ring.
-  for (int direct = 1; direct >= 0; --direct) {
-    for (int nst = direct ? NSTMAX : 3; nst >= (direct ? 4 : 2); --nst) {
+  // Pure Lloyd variant: 2 A stages (load -> convert) + 2 whole-tile M slots for the lane-owns-cluster M-step.
+  // Distance variants: direct mode (the M-step warps read the A ring) when >= 4 stages fit, which covers
+  // load -> convert -> MMA -> epilogue -> M-step; otherwise 2-3 stages plus a quarter-tile M ring.
+  for (int direct = lane_owns ? 0 : 1; direct >= 0; --direct) {
+    const int mr = lane_owns ? BM : MH;
+    for (int nst = direct ? NSTMAX : (lane_owns ? 2 : 3); nst >= (direct ? 4 : 2); --nst) {
       uint32_t o = 0;
       c->off_bhi = o; o += bbytes;
       c->off_blo = o; o += bbytes;
@@ -882,14 +960,16 @@ static bool make_cfg(int d, int k, bool want_dist, TcCfg* c) {
       c->off_c32 = o; if (want_dist) o += (uint32_t)c->NP * c->KB * 128u;   // fp32 centres (distance variants)
       o = (uint32_t)align_up(o, 1024);
       c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring
-      c->off_m = o; if (!direct) o += 2u * c->KB * MKBLK_BYTES;    // M ring
-      c->off_lab = o; o += NLAB * LIST_BYTES;                      // label buffers / per-cluster row lists
+      c->off_m = o; if (!direct) o += 2u * c->KB * mr * 128u;      // M ring
+      c->off_lab = o; o += NLAB * (lane_owns ? LIST_BYTES : BM * 4);   // per-cluster row lists / label buffers
+      c->off_xn = o; o += 4 * BM * 4;                              // ||s x||^2 of the last 4 tiles (converter -> epilogue)
       c->off_red = o; o += (NMW + 1) * 8;
       c->off_bar = o; o += BAR_COUNT * 8;
       c->off_tptr = o; o += 16;
       c->total = o;
       c->NST = nst;
       c->direct = direct;
+      c->MR = mr;
       if (o <= 227 * 1024) return true;
     }
   }
@@ -900,12 +980,11 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
   const bool want_dist = !mstep || a.min_out != nullptr || a.want_sum;
   TcCfg cfg;
-  if (!make_cfg(a.d, a.k, want_dist, &cfg)) return BKM_EUNSUPPORTED;
-  if (mstep && !want_dist && !cfg.direct) return BKM_EUNSUPPORTED;      // the lane-owns-cluster M-step reads the A ring
+  if (!make_cfg(a.d, a.k, mstep, want_dist, &cfg)) return BKM_EUNSUPPORTED;
   CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
   int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
   if (rc) return rc;
-  rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, MH);
+  rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, cfg.MR);
   if (rc) return rc;
   rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dh, a.L.dh, cfg.NP, true);
   if (rc) return rc;

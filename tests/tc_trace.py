@@ -37,3 +37,4 @@ for it in range(lo, hi):
     print("%4d " % it + " ".join("%12d" % (t[s, it] - t0) for s in range(len(names))))
 per = (t[11, hi - 1] - t[11, lo]) / (hi - 1 - lo)
 print("cycles per tile (labels event): %.0f" % per)
+print("M-step warp 0: list-walk iterations per tile:", " ".join(str(int(t[14, it])) for it in range(lo, hi)))
