@@ -518,6 +518,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     const PackHeader* hdr = reinterpret_cast<const PackHeader*>(a.pack);
     const float cnmax = (float)(hdr->cn_max * (double)hdr->scale * (double)hdr->scale);
     const float* xn_s = reinterpret_cast<const float*>(smem + cfg.off_xn);
+    const float one = __uint_as_float(0x3f800000u + ((uint32_t)a.k >> 30));       // 1.0f, -0.0f: not known to the compiler
+    const float nzero = __uint_as_float(0x80000000u + ((uint32_t)a.k >> 30));
 #pragma unroll 1
     for (long long it = set; it < my_tiles; it += 2) {
       const long long tile = blockIdx.x + it * gridDim.x;
@@ -539,6 +541,22 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       float sv[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) sv[i] = CUDART_INF_F;
+// sv[o..o+7] = V[o..o+7] where `better`.  Selects run on the half-rate ALU pipe, which the min tree already
+// loads; a predicated v * 1 + (-0) is exact and runs on the otherwise idle FMA pipe (`one` / `nzero` are
+// opaque run-time registers so that the assembler keeps the FFMA).
+#define PMOV8(S, V, o, B)                                                                              \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %16, 0;\n"                                            \
+               "@p fma.rn.f32 %0, %8, %17, %18;\n@p fma.rn.f32 %1, %9, %17, %18;\n"                     \
+               "@p fma.rn.f32 %2, %10, %17, %18;\n@p fma.rn.f32 %3, %11, %17, %18;\n"                   \
+               "@p fma.rn.f32 %4, %12, %17, %18;\n@p fma.rn.f32 %5, %13, %17, %18;\n"                   \
+               "@p fma.rn.f32 %6, %14, %17, %18;\n@p fma.rn.f32 %7, %15, %17, %18;\n}"                  \
+               : "+f"(S[o + 0]), "+f"(S[o + 1]), "+f"(S[o + 2]), "+f"(S[o + 3]), "+f"(S[o + 4]),       \
+                 "+f"(S[o + 5]), "+f"(S[o + 6]), "+f"(S[o + 7])                                        \
+               : "f"(__uint_as_float(V[o + 0])), "f"(__uint_as_float(V[o + 1])),                       \
+                 "f"(__uint_as_float(V[o + 2])), "f"(__uint_as_float(V[o + 3])),                       \
+                 "f"(__uint_as_float(V[o + 4])), "f"(__uint_as_float(V[o + 5])),                       \
+                 "f"(__uint_as_float(V[o + 6])), "f"(__uint_as_float(V[o + 7])), "r"((int)(B)),        \
+                 "f"(one), "f"(nzero));
 #define EPI_CHUNK(V, COLBASE)                                                            \
   {                                                                                      \
     const float t0 = fmin3(__uint_as_float(V[0]), __uint_as_float(V[1]), __uint_as_float(V[2]));    \
@@ -550,7 +568,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     const bool better = cm < m1;                                                         \
     m2 = fminf(m2, fmaxf(m1, cm));                                                       \
     m1 = fminf(m1, cm);                                                                  \
-    _Pragma("unroll") for (int i = 0; i < 16; ++i) sv[i] = better ? __uint_as_float(V[i]) : sv[i]; \
+    PMOV8(sv, V, 0, better) PMOV8(sv, V, 8, better)                                      \
     sbase = better ? (float)(COLBASE) : sbase;                                           \
   }
 #pragma unroll 1
