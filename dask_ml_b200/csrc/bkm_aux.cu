@@ -137,8 +137,118 @@ __global__ void pack_header_kernel(unsigned char* pack, PackLayout L) {
   }
 }
 
+// Small (k, d) — every shape the tensor path takes — are packed by ONE kernel: each CTA recomputes the two
+// global quantities (max |c| -> scale, all ||c||^2 -> cn_max; k*d is a few thousand elements) and then writes
+// its share of every layout.  Four dependent launches cost more than the work itself.
+__global__ void __launch_bounds__(1024)
+pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L) {
+  extern __shared__ double cn_s[];        // [k]
+  __shared__ double red[32];
+  const int k = L.k, d = L.d, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // ---- max |c| -> scale
+  double m = 0.0;
+#pragma unroll 8
+  for (int i = tid; i < k * d; i += 1024) m = fmax(m, fabs(C[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < 32; ++w) m = fmax(m, red[w]);
+  int e = 0;
+  if (m > 0.0 && m < CUDART_INF) e = 9 - ilogb(m);
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  const double sc = scalbn(1.0, e);
+  __syncthreads();
+  // ---- ||c_j||^2 (one warp per centre, same summation order as pack_norms_kernel) and their maximum
+  for (int j = wid; j < k; j += 32) {
+    double s = 0.0;
+    for (int i = lane; i < d; i += 32) { double v = C[(size_t)j * d + i]; s = fma(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) cn_s[j] = s;
+  }
+  __syncthreads();
+  double cm = 0.0;
+  for (int j = tid; j < k; j += 1024) cm = fmax(cm, cn_s[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+  if (lane == 0) red[wid] = cm;
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {
+    cm = red[0];
+    for (int w = 1; w < 32; ++w) cm = fmax(cm, red[w]);
+    PackHeader* h = reinterpret_cast<PackHeader*>(pack);
+    h->k = k; h->d = d; h->dtype = L.dtype; h->pad = 0; h->cn_max = cm; h->scale = (float)sc; h->pad2 = 0.f;
+  }
+  // ---- this CTA's share of the layouts
+  const int gt = blockIdx.x * 1024 + tid, nth = gridDim.x * 1024;
+  double* c64 = reinterpret_cast<double*>(pack + L.off_c64);
+  for (int i = gt; i < k * d; i += nth) c64[i] = C[i];
+  double* cn64 = reinterpret_cast<double*>(pack + L.off_cn64);
+  if (L.dtype == BKM_F32) {
+    float* cT = reinterpret_cast<float*>(pack + L.off_cT);
+    for (int i = gt; i < k * L.d4; i += nth) {
+      int r = i / L.d4, c = i - r * L.d4;
+      cT[i] = c < d ? (float)C[(size_t)r * d + c] : 0.f;
+    }
+    if (d <= L.dh) {
+      __half* bhi = reinterpret_cast<__half*>(pack + L.off_bhi);
+      __half* blo = reinterpret_cast<__half*>(pack + L.off_blo);
+      for (int i = gt; i < L.kp * L.dh; i += nth) {
+        int r = i / L.dh, c = i - r * L.dh;
+        __half hi = __float2half_rn(0.f), lo = hi;
+        if (r < k && c < d) {
+          const double v = -2.0 * sc * C[(size_t)r * d + c];
+          hi = __double2half(v);
+          lo = __double2half(v - (double)__half2float(hi));
+        }
+        bhi[i] = hi; blo[i] = lo;
+      }
+    }
+    if (L.off_c64T != L.total) {
+      double* cTT = reinterpret_cast<double*>(pack + L.off_c64T);
+      for (int i = gt; i < d * L.kp; i += nth) {
+        int f = i / L.kp, j = i - f * L.kp;
+        cTT[i] = j < k ? C[(size_t)j * d + f] : 0.0;
+      }
+    }
+    float* cn32 = reinterpret_cast<float*>(pack + L.off_cn32);
+    for (int j = gt; j < L.kp; j += nth) {
+      const double s = j < k ? cn_s[j] : 0.0;
+      if (j < k) { cn64[j] = s; reinterpret_cast<float*>(pack + L.off_cnT)[j] = (float)s; }
+      cn32[j] = j < k ? (float)s : CUDART_INF_F;
+      float* bcn = reinterpret_cast<float*>(pack + L.off_bcn) + (j >> 3) * 64 + (j & 7) * 4;
+      float hi = 3.0e38f, mid = 0.f, lo = 0.f;
+      if (j < k) {
+        const float cf = (float)(s * sc * sc);          // the tensor path works on s X and s C
+        hi = to_tf32_rna(cf);
+        const float r1 = cf - hi;
+        mid = to_tf32_rna(r1);
+        lo = r1 - mid;
+      }
+      bcn[0] = hi; bcn[1] = mid; bcn[2] = lo; bcn[3] = 0.f;
+      bcn[32] = 0.f; bcn[33] = 0.f; bcn[34] = 0.f; bcn[35] = 0.f;
+    }
+  } else {
+    double* cT = reinterpret_cast<double*>(pack + L.off_cT);
+    for (int i = gt; i < k * L.d4; i += nth) {
+      int r = i / L.d4, c = i - r * L.d4;
+      cT[i] = c < d ? C[(size_t)r * d + c] : 0.0;
+    }
+    for (int j = gt; j < k; j += nth) { cn64[j] = cn_s[j]; reinterpret_cast<double*>(pack + L.off_cnT)[j] = cn_s[j]; }
+  }
+}
+
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s) {
   PackLayout L = pack_layout(k, d, dtype);
+  if (k <= 2048 && (long long)k * d <= 65536) {
+    int nb = (L.kp * L.dk + 2047) / 2048; if (nb > 16) nb = 16; if (nb < 1) nb = 1;
+    pack_fused_kernel<<<nb, 1024, (size_t)k * 8, s>>>(C, (unsigned char*)pack, L);
+    note_launch();
+    BKM_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   int nb = (L.kp * L.dk + 255) / 256; if (nb > 296) nb = 296; if (nb < 1) nb = 1;
   pack_scale_kernel<<<1, 1024, 0, s>>>(C, (unsigned char*)pack, L);
   pack_centers_kernel<<<nb, 256, 0, s>>>(C, (unsigned char*)pack, L);
@@ -161,22 +271,44 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
                                        double* sums, long long* counts, double* dist_sum) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
+  // The additions run in CTA order (that is what makes a chunk's contribution reproducible); the loads of a
+  // batch are independent, so 16 of them are in flight at a time instead of one.
   if (mstep) {
     for (int i = tid; i < kd; i += nth) {
       double s = 0.0;
-      for (int g = 0; g < sum_parts; ++g) s += (double)psum[(size_t)g * kd + i];
+      int g = 0;
+      for (; g + 16 <= sum_parts; g += 16) {
+        PS v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = psum[(size_t)(g + q) * kd + i];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += (double)v[q];
+      }
+      for (; g < sum_parts; ++g) s += (double)psum[(size_t)g * kd + i];
       sums[i] += s;
     }
-    for (int i = tid; i < k; i += nth) {
+    // counts: the last CTAs take them (the first ones already carry the tail of the sums loop)
+    for (int i = nth - 1 - tid; i < k; i += nth) {
       long long c = 0;
-      for (int g = 0; g < grid; ++g) c += pcnt[(size_t)g * k + i];
+      int g = 0;
+      for (; g + 16 <= grid; g += 16) {
+        int v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = pcnt[(size_t)(g + q) * k + i];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) c += v[q];
+      }
+      for (; g < grid; ++g) c += pcnt[(size_t)g * k + i];
       counts[i] += c;
     }
   }
-  if (tid == 0 && dist_sum) {
+  if (blockIdx.x == 0 && threadIdx.x < 32 && dist_sum) {
+    // lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree: reproducible
     double s = 0.0;
-    for (int g = 0; g < grid; ++g) s += pin[g];
-    *dist_sum += s;
+    for (int g = threadIdx.x; g < grid; g += 32) s += pin[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *dist_sum += s;
   }
 }
 
@@ -200,14 +332,20 @@ int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
 
 // ---------------------------------------------------------------------------------------
 // finalize: C' = sums / max(counts,1) ; shift = ||C - C'||_F^2   (k_means.py:548-555)
-// single CTA, fixed-order reduction -> deterministic shift.
+// up to 64 CTAs; the last one to finish adds the per-CTA parts in CTA order -> deterministic shift
+// (one finalize at a time per device: the scratch is a device global).
 // ---------------------------------------------------------------------------------------
-__global__ void finalize_kernel(const double* __restrict__ sums, const long long* __restrict__ counts,
-                                const double* __restrict__ Cold, double* __restrict__ Cnew,
-                                double* shift, int k, int d) {
+__device__ double g_fin_part[64];
+__device__ unsigned int g_fin_done = 0;
+
+__global__ void __launch_bounds__(1024)
+finalize_kernel(const double* __restrict__ sums, const long long* __restrict__ counts,
+                const double* __restrict__ Cold, double* __restrict__ Cnew,
+                double* shift, int k, int d) {
   __shared__ double sm[32];
+  __shared__ bool last;
   double acc = 0.0;
-  for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k * d; i += gridDim.x * blockDim.x) {
     int j = i / d;
     long long c = counts[j];
     double cn = sums[i] / (double)(c > 1 ? c : 1);
@@ -222,13 +360,25 @@ __global__ void finalize_kernel(const double* __restrict__ sums, const long long
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
+    g_fin_part[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(&g_fin_done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    // the last CTA to finish adds the per-CTA parts in CTA order: deterministic shift
+    __threadfence();
+    double s = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += *(volatile double*)&g_fin_part[b];
     *shift = s;
+    g_fin_done = 0;
   }
 }
 
 int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
                     double* shift, int k, int d, cudaStream_t s) {
-  finalize_kernel<<<1, 1024, 0, s>>>(sums, counts, Cold, Cnew, shift, k, d);
+  int nb = (k * d + 1023) / 1024; if (nb > 64) nb = 64; if (nb < 1) nb = 1;
+  finalize_kernel<<<nb, 1024, 0, s>>>(sums, counts, Cold, Cnew, shift, k, d);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;

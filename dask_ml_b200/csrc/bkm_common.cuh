@@ -31,7 +31,7 @@ struct PackLayout {
   int dk;      // d rounded up to a multiple of 32 (one 128-byte swizzle atom of fp32 per K-block)
   int dh;      // row length of the fp16 MMA operand tiles: 64 halves = one 128-byte swizzle atom (d <= 64)
   size_t esz;  // sizeof(T)
-  size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, off_bcn, total;
+  size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, off_bcn, off_c64T, total;
 };
 
 static inline PackLayout pack_layout(int k, int d, int dtype) {
@@ -51,6 +51,8 @@ static inline PackLayout pack_layout(int k, int d, int dtype) {
   L.off_blo = o;  o = align_up(o + (size_t)L.kp * L.dh * 2, 256);
   L.off_cn32 = o; o = align_up(o + (size_t)L.kp * 4, 256);
   L.off_bcn = o;  o = align_up(o + (size_t)L.kp * 32, 256);   // ||c||^2 as an MMA operand tile (see bkm_tc.cu)
+  // float64 centres transposed [d][kp] for the float64 re-check of the tensor path (coalesced over centres)
+  L.off_c64T = o; if (dtype == BKM_F32 && d <= 64 && k <= 256) o = align_up(o + (size_t)d * L.kp * 8, 256);
   L.total = o;
   return L;
 }

@@ -831,71 +831,95 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 }
 
 // ------------------------------------------------------------------------------------------
-// Deferred float64 re-check.  Rows whose 3xTF32 best/second margin was inside the rounding bound
-// were left out of the fused kernel's outputs and M-step; here they are decided exactly:
-// d2_j = sum_i (x_i - c_ji)^2 in float64 against the float64 centres (transposed in shared memory so
-// that thread j <-> centre j reads are conflict-free), lowest index on exact ties.  Their labels,
+// Deferred float64 re-check.  Rows whose best/second margin was inside the rounding bound of the split-fp16
+// product (or whose scaled entries left fp16's range) were left out of the fused kernel's outputs and M-step;
+// here they are decided exactly: d2_j = sum_i (x_i - c_ji)^2 in float64 against the float64 centres
+// (transposed, so that thread j <-> centre j reads are coalesced / conflict-free), lowest index on exact ties.  Their labels,
 // distances and M-step contributions are then added (float64 atomics: order-insensitive to ~1e-16).
 // ------------------------------------------------------------------------------------------
+static const int RCK_ROWS = 8;      // deferred rows decided together by one CTA (the centres are read once per group)
+
 __global__ void __launch_bounds__(256)
 tc_recheck_kernel(ChunkArgs a, bool mstep, double* sums, unsigned long long* counts, double* dist_sum) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ float xs[RCK_ROWS][64];
+  __shared__ double wd[RCK_ROWS][8];
+  __shared__ int wj[RCK_ROWS][8];
+  __shared__ long long rows_s[RCK_ROWS];
   const int cnt = *a.defer_cnt;
-  if ((int)blockIdx.x >= cnt) return;
-  const int k = a.k, d = a.d, tid = threadIdx.x;
-  const int kpad = (k + 31) / 32 * 32 + 1;                 // odd pitch: conflict-free transpose writes
-  double* cT = reinterpret_cast<double*>(smem);             // [d][kpad]
-  float* xrow = reinterpret_cast<float*>(smem + (size_t)d * kpad * 8);   // [d]
-  double* wd = reinterpret_cast<double*>(xrow + ((d + 3) & ~3));         // [8]
-  int* wj = reinterpret_cast<int*>(wd + 8);                               // [8]
-  const double* gC64 = reinterpret_cast<const double*>(a.pack + a.L.off_c64);
-  for (int e = tid; e < k * d; e += 256) { const int j = e / d, i = e - j * d; cT[i * kpad + j] = gC64[e]; }
+  if ((int)blockIdx.x * RCK_ROWS >= cnt) return;
+  const int k = a.k, d = a.d, tid = threadIdx.x, kp = a.L.kp, lane = tid & 31, wid = tid >> 5;
+  // float64 centres, transposed [d][kp] by the pack: thread j <-> centre j reads are coalesced and hit L2
+  // (every CTA reads the same 128 KB).
+  const double* gT = reinterpret_cast<const double*>(a.pack + a.L.off_c64T);
   const float* X = reinterpret_cast<const float*>(a.X);
-  for (int f = blockIdx.x; f < cnt; f += gridDim.x) {
-    const long long row = a.defer_idx[f];
+  for (int f0 = blockIdx.x * RCK_ROWS; f0 < cnt; f0 += gridDim.x * RCK_ROWS) {
+    const int nr = min(RCK_ROWS, cnt - f0);
     __syncthreads();
-    for (int i = tid; i < d; i += 256) xrow[i] = X[row * a.ldx + i];
+    if (tid < RCK_ROWS) rows_s[tid] = tid < nr ? (long long)a.defer_idx[f0 + tid] : -1;
     __syncthreads();
-    double bd = CUDART_INF; int bj = 0x7fffffff;
-    for (int j = tid; j < k; j += 256) {
-      double s0 = 0.0, s1 = 0.0;
+    for (int e = tid; e < RCK_ROWS * 64; e += 256) {
+      const int r = e >> 6, i = e & 63;
+      xs[r][i] = (r < nr && i < d) ? X[rows_s[r] * a.ldx + i] : 0.f;
+    }
+    __syncthreads();
+    // thread j: squared distances of the group's rows to centre j (two interleaved partial sums per row: the
+    // order of the float64 additions is fixed, sum of even features + sum of odd features)
+    double s0[RCK_ROWS], s1[RCK_ROWS];
+#pragma unroll
+    for (int r = 0; r < RCK_ROWS; ++r) { s0[r] = 0.0; s1[r] = 0.0; }
+    const int j = tid;
+    if (j < k) {
       int i = 0;
       for (; i + 1 < d; i += 2) {
-        const double d0 = (double)xrow[i] - cT[i * kpad + j];
-        const double d1 = (double)xrow[i + 1] - cT[(i + 1) * kpad + j];
-        s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
+        const double c0 = gT[(size_t)i * kp + j], c1 = gT[(size_t)(i + 1) * kp + j];
+#pragma unroll
+        for (int r = 0; r < RCK_ROWS; ++r) {
+          const double d0 = (double)xs[r][i] - c0, d1 = (double)xs[r][i + 1] - c1;
+          s0[r] = fma(d0, d0, s0[r]); s1[r] = fma(d1, d1, s1[r]);
+        }
       }
-      if (i < d) { const double d0 = (double)xrow[i] - cT[i * kpad + j]; s0 = fma(d0, d0, s0); }
-      const double sdist = s0 + s1;
-      if (sdist < bd) { bd = sdist; bj = j; }
+      if (i < d) {
+        const double c0 = gT[(size_t)i * kp + j];
+#pragma unroll
+        for (int r = 0; r < RCK_ROWS; ++r) { const double d0 = (double)xs[r][i] - c0; s0[r] = fma(d0, d0, s0[r]); }
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-      if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+    for (int r = 0; r < RCK_ROWS; ++r) {
+      double bd = j < k ? s0[r] + s1[r] : CUDART_INF;
+      int bj = j < k ? j : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+      }
+      if (lane == 0) { wd[r][wid] = bd; wj[r][wid] = bj; }
     }
-    if ((tid & 31) == 0) { wd[tid >> 5] = bd; wj[tid >> 5] = bj; }
     __syncthreads();
-    double fd = wd[0]; int fj = wj[0];
-    for (int w = 1; w < 8; ++w) if (wd[w] < fd || (wd[w] == fd && wj[w] < fj)) { fd = wd[w]; fj = wj[w]; }
-    if (tid == 0) {
+    if (tid < nr) {
+      const int r = tid;
+      double fd = wd[r][0]; int fj = wj[r][0];
+      for (int w = 1; w < 8; ++w) if (wd[r][w] < fd || (wd[r][w] == fd && wj[r][w] < fj)) { fd = wd[r][w]; fj = wj[r][w]; }
+      const long long row = rows_s[r];
       const double outv = a.squared ? fd : sqrt(fd);
       if (a.labels) a.labels[row] = fj;
       if (a.min_out) reinterpret_cast<float*>(a.min_out)[row] = (float)outv;
       if (dist_sum) atomicAdd(dist_sum, outv);
       if (mstep) atomicAdd(counts + fj, 1ull);
+      wj[r][0] = fj;
     }
-    if (mstep) for (int i = tid; i < d; i += 256) atomicAdd(sums + (size_t)fj * d + i, (double)xrow[i]);
+    __syncthreads();
+    if (mstep)
+      for (int e = tid; e < nr * 64; e += 256) {
+        const int r = e >> 6, i = e & 63;
+        if (i < d) atomicAdd(sums + (size_t)wj[r][0] * d + i, (double)xs[r][i]);
+      }
   }
 }
 
 static int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t s) {
-  const int kpad = (a.k + 31) / 32 * 32 + 1;
-  const size_t smem = (size_t)a.d * kpad * 8 + (size_t)((a.d + 3) & ~3) * 4 + 8 * 8 + 8 * 4 + 16;
-  if (smem > 227 * 1024) return BKM_EUNSUPPORTED;
-  BKM_CUDA_TRY(cudaFuncSetAttribute(tc_recheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_recheck_kernel<<<sm_count, 256, smem, s>>>(a, mstep, a.out_sums, (unsigned long long*)a.out_counts, a.out_dist_sum);
+  tc_recheck_kernel<<<sm_count * 4, 256, 0, s>>>(a, mstep, a.out_sums, (unsigned long long*)a.out_counts, a.out_dist_sum);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;
