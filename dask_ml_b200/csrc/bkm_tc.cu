@@ -70,10 +70,12 @@ enum {
   BAR_X_FULL = 1,                          // [NSTMAX]
   BAR_X_EMPTY = BAR_X_FULL + NSTMAX,       // [NSTMAX]
   BAR_ACC_FULL = BAR_X_EMPTY + NSTMAX,     // [set 2][buf 3]  one barrier per (epilogue warp set, accumulator buffer): every
-  BAR_ACC_EMPTY = BAR_ACC_FULL + 6,        // [set 2][buf 3]  waiter then observes consecutive phases (no parity aliasing)
-  BAR_XOP_FULL = BAR_ACC_EMPTY + 6,        // [4]   X operands (and ||x||^2) of tile it are ready; indexed it & 3 so that
-                                           //       the epilogue's late acquire cannot alias a newer phase
-  BAR_XOP_EMPTY = BAR_XOP_FULL + 4,        // [2]   ... and the MMAs that read them have completed
+  BAR_ACC_EMPTY = BAR_ACC_FULL + 6,        // [set 2][buf 3][issuer 2]  waiter then observes consecutive phases (a parity wait
+                                           //   that is asked before the PREVIOUS phase has completed succeeds spuriously)
+  BAR_XOP_FULL = BAR_ACC_EMPTY + 12,       // [8]   X operands (and ||x||^2) of tile it are ready; indexed it & 7: the converter can
+                                           //       run up to 6 tiles ahead of a late epilogue set (one-unit tiles), and a wait that
+                                           //       is asked after the NEXT phase has completed as well would never return
+  BAR_XOP_EMPTY = BAR_XOP_FULL + 8,        // [2]   ... and the MMAs that read them have completed
   BAR_LAB_FULL = BAR_XOP_EMPTY + 2,        // [NLAB]
   BAR_LAB_EMPTY = BAR_LAB_FULL + NLAB,     // [NLAB]
   BAR_M_FULL = BAR_LAB_EMPTY + NLAB,       // [2]  M ring (ring mode): 32-row quarter tiles re-fetched (L2 hits)
@@ -125,7 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // suspend-time hint: the hardware
         "selp.u32 %0, 1, 0, p;\n}"                                        // parks the warp instead of polling
         : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
-    if (spin > (1u << 18) || ((spin & 1023) == 1023 && *(volatile unsigned int*)&g_tc_abort)) {
+    if (spin > (1u << 18) || ((spin & 15) == 15 && *(volatile unsigned int*)&g_tc_abort)) {
       atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
       if (spin > 2048 && (threadIdx.x & 31) == 0) g_tc_dbg[threadIdx.x >> 5] = 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | blockIdx.x;
       return;
@@ -152,7 +154,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (!done) __nanosleep(256);
-    if (spin > (1u << 20) || ((spin & 255) == 255 && *(volatile unsigned int*)&g_tc_abort)) {
+    if (spin > (1u << 20) || ((spin & 15) == 15 && *(volatile unsigned int*)&g_tc_abort)) {
       atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
       return;
     }
@@ -275,13 +277,13 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     }
     for (int b = 0; b < 2 * NBUF; ++b) {
       mbar_init(BAR(BAR_ACC_FULL + b), 1);
-      mbar_init(BAR(BAR_ACC_EMPTY + b), 128);
+      mbar_init(BAR(BAR_ACC_EMPTY + 2 * b), 128);
+      mbar_init(BAR(BAR_ACC_EMPTY + 2 * b + 1), 128);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(BAR_M_FULL + b), 1);
       mbar_init(BAR(BAR_M_EMPTY + b), NMWK);
-      mbar_init(BAR(BAR_XOP_FULL + b), 128);
-      mbar_init(BAR(BAR_XOP_FULL + 2 + b), 128);
+      for (int q = 0; q < 4; ++q) mbar_init(BAR(BAR_XOP_FULL + 4 * b + q), 128);
       mbar_init(BAR(BAR_XOP_EMPTY + b), (uint32_t)U);
     }
     for (int b = 0; b < NLAB; ++b) {
@@ -411,6 +413,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     const uint64_t dcn = dns | (uint64_t)(((sbase + cfg.off_bcn) >> 4) & 0x3FFF);
     const uint64_t dones = dns | (uint64_t)(((sbase + cfg.off_ones) >> 4) & 0x3FFF);
     const long long g_total = my_tiles * U;
+    uint32_t empty_ph = 0;      // phase bit of each accumulator-empty barrier this issuer waits on
 #pragma unroll 1
     for (long long g = warp - 1; g < g_total; g += 2) {
       const long long it = U == 2 ? (g >> 1) : g;
@@ -421,11 +424,14 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       const uint32_t xlo_t = tmem + TM_XLO + (uint32_t)(it & 1) * 32u;
       const int buf = (int)(g % NBUF);
       if (g >= NBUF) {
-        // the buffer was last used by unit g-NBUF, consumed by epilogue set ((g-NBUF)/U) & 1
+        // the buffer was last used by unit g-NBUF, drained by epilogue set ((g-NBUF)/U) & 1, which signals the
+        // barrier of (its set, the buffer, the issuer of the buffer's next unit = this warp)
         const long long gp = g - NBUF;
-        mbar_wait(BAR(BAR_ACC_EMPTY + (int)((gp / U) & 1) * NBUF + buf), acc_parity(gp, U));
+        const int eb = (int)((gp / U) & 1) * NBUF + buf;
+        mbar_wait(BAR(BAR_ACC_EMPTY + 2 * eb + (warp - 1)), (empty_ph >> eb) & 1u);
+        empty_ph ^= 1u << eb;
       }
-      mbar_wait(BAR(BAR_XOP_FULL + (it & 3)), (uint32_t)((it >> 2) & 1));
+      mbar_wait(BAR(BAR_XOP_FULL + (it & 7)), (uint32_t)((it >> 3) & 1));
       tc_fence_after();
       if (leader) TRACE(3 + 2 * u, it);
       const int ncols = u == 0 ? cfg.NU0 : cfg.NU1;
@@ -463,7 +469,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     const int r = q4 * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     const float sc = reinterpret_cast<const PackHeader*>(a.pack)->scale;
-    float* xn_s = reinterpret_cast<float*>(smem + cfg.off_xn);       // [4][BM]
+    float* xn_s = reinterpret_cast<float*>(smem + cfg.off_xn);       // [8][BM]
     uint32_t xoff[8];                              // swizzled 16-byte chunk offsets of this thread's row
 #pragma unroll
     for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
@@ -500,11 +506,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         TC_ST16S(tmem + lane_addr + TM_XHI + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 0);
         TC_ST16S(tmem + lane_addr + TM_XLO + (uint32_t)(it & 1) * 32u + (uint32_t)kb * 16u, v, 1);
       }
-      xn_s[(it & 3) * BM + r] = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
+      xn_s[(it & 7) * BM + r] = (xn4[0] + xn4[1]) + (xn4[2] + xn4[3]);
       mbar_arrive(BAR(BAR_X_EMPTY + stage));        // the converter is done with the smem stage
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(BAR(BAR_XOP_FULL + (it & 3)));      // release: also publishes xn_s
+      mbar_arrive(BAR(BAR_XOP_FULL + (it & 7)));      // release: also publishes xn_s
       if (r == 0) TRACE(2, it);
     }
   } else if (warp >= 8 && warp < MW0) {
@@ -524,8 +530,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     for (long long it = set; it < my_tiles; it += 2) {
       const long long tile = blockIdx.x + it * gridDim.x;
       // the converter published ||s x||^2 before it released the operands (completed long ago: acquire only)
-      mbar_wait(BAR(BAR_XOP_FULL + (it & 3)), (uint32_t)((it >> 2) & 1));
-      const float xn = xn_s[(it & 3) * BM + r];
+      mbar_wait(BAR(BAR_XOP_FULL + (it & 7)), (uint32_t)((it >> 3) & 1));
+      const float xn = xn_s[(it & 7) * BM + r];
       const float bound = a.tau * (xn + cnmax);
       // an entry beyond fp16's range (|s x| >= 65504 => xn >= 4.29e9) or a non-finite one: float64 path
       const bool out_of_range = !(xn < 4.29e9f);
@@ -596,7 +602,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
           }
         }
         tc_fence_before();
-        mbar_arrive(BAR(BAR_ACC_EMPTY + set * NBUF + buf));
+        mbar_arrive(BAR(BAR_ACC_EMPTY + 2 * (set * NBUF + buf) + (int)((g + NBUF) & 1)));    // -> issuer of unit g + NBUF
         if (r == 0) TRACE(8 + 2 * u, it);
       }
 #undef EPI_CHUNK
@@ -665,8 +671,9 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #if BKM_TRACE
       int witers = 0;
 #endif
+      int guard = BM;                                 // a list holds at most the tile's rows (a corrupted list must not spin)
 #pragma unroll 1
-      while (__any_sync(0xffffffffu, rr >= 0)) {
+      while (__any_sync(0xffffffffu, rr >= 0) && guard-- > 0) {
 #if BKM_TRACE
         ++witers;
 #endif
@@ -1004,7 +1011,7 @@ static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {
       c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring
       c->off_m = o; if (!direct) o += 2u * c->KB * mr * 128u;      // M ring
       c->off_lab = o; o += NLAB * (lane_owns ? LIST_BYTES : BM * 4);   // per-cluster row lists / label buffers
-      c->off_xn = o; o += 4 * BM * 4;                              // ||s x||^2 of the last 4 tiles (converter -> epilogue)
+      c->off_xn = o; o += 8 * BM * 4;                              // ||s x||^2 of the last 8 tiles (converter -> epilogue)
       c->off_red = o; o += (NMW + 1) * 8;
       c->off_bar = o; o += BAR_COUNT * 8;
       c->off_tptr = o; o += 16;

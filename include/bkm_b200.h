@@ -66,7 +66,7 @@ const char* bkm_error_string(int code);
 int bkm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
 /* Which kernel family a (d, k, dtype, flags) problem dispatches to:
- * 0 = SIMT (CUDA cores, fp32/fp64 exact), 1 = tcgen05 3xTF32 tensor-core path. <0 = error. */
+ * 0 = SIMT (CUDA cores, fp32/fp64 exact), 1 = tcgen05 tensor-core path (split-fp16 x3 product, fp32 accumulate). <0 = error. */
 int bkm_kernel_family(int d, int k, int x_dtype, int flags);
 
 /* ---- centre pack -------------------------------------------------------------------

@@ -172,3 +172,97 @@ def test_check_finite(be):
     assert int(be.check_finite([be.to_device(X, torch.float32)]).item()) != 0
     X[4321, 3] = np.nan
     assert int(be.check_finite([be.to_device(X, torch.float64)]).item()) != 0
+
+
+def _exact_labels_f64(x, C):
+    """float64 arg-min on the device, in row blocks (sizes the CPU oracle would take minutes for)."""
+    import torch
+
+    C64 = C.double()
+    cn = (C64 * C64).sum(1)
+    out = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
+    second = torch.empty((x.shape[0],), dtype=torch.float64, device=x.device)
+    for s in range(0, x.shape[0], 1 << 18):
+        xb = x[s:s + (1 << 18)].double()
+        d2 = (xb * xb).sum(1, keepdim=True) + cn[None, :] - 2.0 * xb @ C64.T
+        if C64.shape[0] > 1:
+            top = torch.topk(d2, 2, dim=1, largest=False)
+            out[s:s + xb.shape[0]] = top.indices[:, 0]
+            second[s:s + xb.shape[0]] = top.values[:, 1] - top.values[:, 0]
+        else:
+            out[s:s + xb.shape[0]] = 0
+            second[s:s + xb.shape[0]] = 1.0
+    return out, second
+
+
+# Pipeline stress of the tcgen05 kernels: row counts that leave every kind of tail (fewer tiles than SMs, one
+# tile more on some SMs, a partial last tile), both kernel variants (pure Lloyd = lane-owns-cluster M-step with
+# the whole-tile M ring; with distances = quarter-tile ring), one and two accumulator units.
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 148 * 128 - 1, 148 * 128 * 3 + 77, 200_000, 1_000_003])
+@pytest.mark.parametrize("d,k", [(64, 256), (64, 100), (32, 130), (8, 16)])
+@pytest.mark.parametrize("want_dist", [False, True])
+def test_tcgen05_pipeline_tails(be, n, d, k, want_dist):
+    import torch
+
+    if be.kernel_family(d, k, torch.float32) != 1:
+        pytest.skip("shape not on the tensor path")
+    g = torch.Generator(device=be.device).manual_seed(n + d + k)
+    cent = torch.empty((max(2, k // 2), d), device=be.device).uniform_(-10, 10, generator=g)
+    X = cent[torch.randint(0, cent.shape[0], (n,), device=be.device, generator=g)] + \
+        torch.randn((n, d), device=be.device, generator=g)
+    C = X[torch.randint(0, n, (k,), device=be.device, generator=g)].double() + \
+        0.01 * torch.randn((k, d), device=be.device, generator=g, dtype=torch.float64)
+    pack = be.pack_centers(C.contiguous(), torch.float32)
+    labels = be.empty((n,), torch.int32)
+    mind2 = be.empty((n,), torch.float32) if want_dist else None
+    sums = be.zeros((k * d,), torch.float64)
+    counts = be.zeros((k,), torch.int64)
+    inertia = be.zeros((1,), torch.float64) if want_dist else None
+    for _ in range(2):          # twice: the second launch reuses every barrier / list / ring of a warm SM
+        sums.zero_(); counts.zero_()
+        if inertia is not None:
+            inertia.zero_()
+        be.lloyd_chunk(X, pack, k, labels, mind2, sums, counts, inertia)
+    torch.cuda.synchronize()
+    assert be.lib.bkm_debug_abort_code() == 0
+    want, margin = _exact_labels_f64(X, C)
+    got = labels.long()
+    bad = got != want
+    # a label may differ from the float64 arg-min only where float64 itself is (nearly) tied
+    if bool(bad.any()):
+        xs = (X.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
+        assert bool((margin[bad] <= 1e-9 * xs).all()), int(bad.sum())
+    assert torch.equal(counts, torch.bincount(got, minlength=k))
+    ref = torch.zeros((k, d), dtype=torch.float64, device=be.device).index_add_(0, got, X.double())
+    assert float((sums.view(k, d) - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) + 1e-9
+
+
+def test_tcgen05_out_of_range_and_mixed_scales(be):
+    """Rows far outside the centres' range (beyond fp16 after scaling), features of very different scale and
+    non-finite entries must take the float64 path and still give the float64 labels."""
+    import torch
+
+    n, d, k = 50_000, 64, 256
+    g = torch.Generator(device=be.device).manual_seed(7)
+    fscale = torch.logspace(-6, 3, d, device=be.device)                 # features from 1e-6 to 1e3
+    cent = torch.empty((k, d), device=be.device).uniform_(-1, 1, generator=g) * fscale
+    X = cent[torch.randint(0, k, (n,), device=be.device, generator=g)] + \
+        0.05 * fscale * torch.randn((n, d), device=be.device, generator=g)
+    X[::97] *= 3000.0                                                    # far beyond 64x the largest centre entry
+    X[5, 3] = 3.0e38
+    C = X[torch.randperm(n, device=be.device, generator=g)[:k] | 1].double().contiguous()   # odd rows: none of the scaled ones
+    pack = be.pack_centers(C, torch.float32)
+    labels = be.empty((n,), torch.int32)
+    sums = be.zeros((k * d,), torch.float64)
+    counts = be.zeros((k,), torch.int64)
+    be.lloyd_chunk(X, pack, k, labels, None, sums, counts, None)
+    torch.cuda.synchronize()
+    assert be.lib.bkm_debug_abort_code() == 0
+    want, margin = _exact_labels_f64(X, C)
+    got = labels.long()
+    bad = got != want
+    bad[5] = False                                                       # the overflowing row has no float64 answer either
+    if bool(bad.any()):
+        xs = (X.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
+        assert bool((margin[bad] <= 1e-9 * xs).all()), int(bad.sum())
+    assert int(counts.sum()) == n
