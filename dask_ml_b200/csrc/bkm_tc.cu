@@ -36,10 +36,10 @@ static const int BM = 128;           // rows per tile
 // Roles are assigned per aligned group of 4 warps (setmaxnreg moves registers between whole warpgroups):
 // warps 0-3: TMA producer (0), MMA issuer (1), 2 spare; 4-7 converter; 8-11 / 12-15 epilogue sets; 16+ M-step
 static const int MW0 = 16;
-static const int NMW = 16;               // distance variants: 16 distance + M-step warps (warp owns the clusters c % 16)
-static const int NMW_LANE = 8;           // pure Lloyd variant: 8 M-step warps, LANE j of warp w owns cluster 32 w + j
+static const int NMW = 16;               // sums AND distances in one pass: 16 distance + M-step warps (warp owns the clusters c % 16)
+static const int NMW_LANE = 8;           // every other variant: 8 warps, LANE j of warp w owns cluster 32 w + j (its sums or its centre)
 static const int LIST_BYTES = 256 * 4 + BM * 4;   // per label buffer: head[256] + next[128] (row lists per cluster)
-__host__ __device__ constexpr int tc_mwarps(bool mstep, bool want_dist) { return (mstep && !want_dist) ? NMW_LANE : NMW; }
+__host__ __device__ constexpr int tc_mwarps(bool mstep, bool want_dist) { return (mstep && want_dist) ? NMW : NMW_LANE; }
 // register cap: registers are allocated per warp in units of 512 (16 per thread)
 // (each of the 4 SM sub-partitions holds 16384 registers and ceil(warps / 4) of the CTA's warps)
 __host__ __device__ constexpr int tc_maxreg(bool mstep, bool want_dist) { return 16384 / ((MW0 + tc_mwarps(mstep, want_dist) + 3) / 4) / 512 * 16; }
@@ -55,7 +55,8 @@ struct TcCfg {
   int NU0, NU1;  // columns of unit 0 / unit 1 (NU1 == 0 -> one unit per tile)
   int U;
   int NST;       // X stages
-  int direct;    // 1: the M-step warps read the A ring; 0: separate M ring
+  int direct;    // 1: the (warp-owns-clusters) M-step warps read the A ring
+  int mring;     // 1: separate M ring (quarter-tile or whole-tile slots)
   int MR;        // rows per M-ring slot (32: quarter tiles, 128: whole tiles)
   uint32_t off_bhi, off_blo, off_bcn, off_ones, off_c32, off_x, off_m, off_lab, off_xn, off_red, off_bar, off_tptr, total;
 };
@@ -244,7 +245,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
                 const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
                 const __grid_constant__ CUtensorMap tm_xm) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr bool LANE_OWNS = MSTEP && !WANT_DIST;     // M-step flavour (see the two M-step blocks below)
+  constexpr bool LANE_OWNS = !(MSTEP && WANT_DIST);   // M-step flavour (see the two M-step blocks below)
+  constexpr bool HAS_M = MSTEP || WANT_DIST;          // labels-only assignment has no M-step / distance stage at all
   constexpr int NMWK = tc_mwarps(MSTEP, WANT_DIST);
   constexpr int NTHREADS = tc_threads(MSTEP, WANT_DIST);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -308,12 +310,12 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     for (int i = tid; i < BM * 2; i += NTHREADS)
       odst[i] = ((i >> 3) & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(1.f, 1.f, 1.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (LANE_OWNS) {
+    if (LANE_OWNS && HAS_M) {
       // row lists: every head starts empty
       int* hd = reinterpret_cast<int*>(smem + cfg.off_lab);
       for (int i = tid; i < NLAB * (LIST_BYTES / 4); i += NTHREADS) hd[i] = -1;
     }
-    if (WANT_DIST) {
+    if (WANT_DIST && !LANE_OWNS) {
       // fp32 centres [NP][KB*32] for the exact direct-form winning distance (rows >= k / columns >= d: zero)
       const float* gc = reinterpret_cast<const float*>(a.pack + a.L.off_cT);      // [k][d4]
       float* cdst = reinterpret_cast<float*>(smem + cfg.off_c32);
@@ -355,7 +357,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       const int qpt = BM / MR;                            // slots per tile
       const uint32_t mkblk = (uint32_t)MR * 128u;
       const uint32_t mbytes = (uint32_t)KB * mkblk;
-      const long long m_total = direct ? 0 : qpt * my_tiles;
+      const long long m_total = cfg.mring ? qpt * my_tiles : 0;
       long long ait = 0, mi = 0;
       uint32_t idle = 0;
 #pragma unroll 1
@@ -626,7 +628,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         const int slot = atomicAdd(a.defer_cnt, 1);
         a.defer_idx[slot] = (int)row;
       }
-      {
+      if (HAS_M) {
         const int lb = (int)(it % NLAB);
         mbar_wait(BAR(BAR_LAB_EMPTY + lb), (uint32_t)(((it / NLAB) & 1) ^ 1));
         if (LANE_OWNS) {
@@ -643,7 +645,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   } else if (warp >= MW0 && LANE_OWNS) {
     REG_INC(104);
     // =========================== M-step warps, lane-owns-cluster flavour ===========================
-    // Lane j of warp w owns cluster c = 32 w + j and keeps its d partial sums in registers.  The rows come
+    // Lane j of warp w owns cluster c = 32 w + j and keeps its d partial sums (or, when only distances are
+    // wanted, its centre) in registers.  The rows come
     // from the M ring (two full-tile slots, re-fetched from L2 while the tile's epilogue runs), so the A ring
     // only has to cover load -> convert and two stages are enough.  The epilogue
     // threads have linked the tile's rows into one list per cluster (head[c] -> next[row] -> ...); every lane
@@ -652,67 +655,97 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     // and 64 independent adds per row instead of a dependent chain per row.
     const int wm = warp - MW0;
     const int c = wm * 32 + lane;
-    float acc[64];
+    double dsum = 0.0;
+    if (HAS_M) {
+      // MSTEP: the running sums of cluster c.  Distance variant: the fp32 centre c itself, so that the winning
+      // distance of every row of the list is evaluated in direct form sum (x - c)^2 without leaving the lane.
+      float acc[64];
+      if (MSTEP) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    int cnt = 0;
-    const bool two = KB > 1;
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      } else {
+        const float* gc = reinterpret_cast<const float*>(a.pack + a.L.off_cT) + (size_t)(c < a.k ? c : 0) * a.L.d4;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = (c < a.k && i < a.d) ? gc[i] : 0.f;
+      }
+      int cnt = 0;
+      const bool two = KB > 1;
 #pragma unroll 1
-    for (long long it = 0; it < my_tiles; ++it) {
-      const int lb = (int)(it % NLAB);
-      const int slot = (int)(it & 1);
-      mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it / NLAB) & 1));
-      mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((it >> 1) & 1));
-      if (wm == 0 && lane == 0) TRACE(12, it);
-      int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
-      const unsigned char* xs = smem + cfg.off_m + slot * stage_bytes;      // full-tile slot: same layout as an A stage
-      int rr = head[c];
-      head[c] = -1;
-#if BKM_TRACE
-      int witers = 0;
-#endif
-      int guard = BM;                                 // a list holds at most the tile's rows (a corrupted list must not spin)
+      for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const int lb = (int)(it % NLAB);
+        const int slot = (int)(it & 1);
+        mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it / NLAB) & 1));
+        mbar_wait(BAR(BAR_M_FULL + slot), (uint32_t)((it >> 1) & 1));
+        if (wm == 0 && lane == 0) TRACE(12, it);
+        int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
+        const unsigned char* xs = smem + cfg.off_m + slot * stage_bytes;      // full-tile slot: same layout as an A stage
+        int rr = head[c];
+        head[c] = -1;
+        int guard = BM;                                 // a list holds at most the tile's rows (a corrupted list must not spin)
 #pragma unroll 1
-      while (__any_sync(0xffffffffu, rr >= 0) && guard-- > 0) {
-#if BKM_TRACE
-        ++witers;
-#endif
-        if (rr >= 0) {
-          const unsigned char* xr = xs + rr * 128;
-          const int sw = rr & 7;
+        while (__any_sync(0xffffffffu, rr >= 0) && guard-- > 0) {
+          if (rr >= 0) {
+            const unsigned char* xr = xs + rr * 128;
+            const int sw = rr & 7;
+            if (MSTEP) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(xr + ((q ^ sw) << 4));
-            acc[q * 4 + 0] += t.x; acc[q * 4 + 1] += t.y; acc[q * 4 + 2] += t.z; acc[q * 4 + 3] += t.w;
-          }
-          if (two) {
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(xr + ((q ^ sw) << 4));
+                acc[q * 4 + 0] += t.x; acc[q * 4 + 1] += t.y; acc[q * 4 + 2] += t.z; acc[q * 4 + 3] += t.w;
+              }
+              if (two) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t = *reinterpret_cast<const float4*>(xr + KBLK_BYTES + ((q ^ sw) << 4));
-              acc[32 + q * 4 + 0] += t.x; acc[32 + q * 4 + 1] += t.y; acc[32 + q * 4 + 2] += t.z; acc[32 + q * 4 + 3] += t.w;
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t = *reinterpret_cast<const float4*>(xr + KBLK_BYTES + ((q ^ sw) << 4));
+                  acc[32 + q * 4 + 0] += t.x; acc[32 + q * 4 + 1] += t.y; acc[32 + q * 4 + 2] += t.z; acc[32 + q * 4 + 3] += t.w;
+                }
+              }
+              ++cnt;
+            } else {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(xr + ((q ^ sw) << 4));
+                const float e0 = t.x - acc[q * 4 + 0], e1 = t.y - acc[q * 4 + 1];
+                const float e2 = t.z - acc[q * 4 + 2], e3 = t.w - acc[q * 4 + 3];
+                s0 = fmaf(e0, e0, s0); s1 = fmaf(e1, e1, s1); s2 = fmaf(e2, e2, s2); s3 = fmaf(e3, e3, s3);
+              }
+              if (two) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t = *reinterpret_cast<const float4*>(xr + KBLK_BYTES + ((q ^ sw) << 4));
+                  const float e0 = t.x - acc[32 + q * 4 + 0], e1 = t.y - acc[32 + q * 4 + 1];
+                  const float e2 = t.z - acc[32 + q * 4 + 2], e3 = t.w - acc[32 + q * 4 + 3];
+                  s0 = fmaf(e0, e0, s0); s1 = fmaf(e1, e1, s1); s2 = fmaf(e2, e2, s2); s3 = fmaf(e3, e3, s3);
+                }
+              }
+              const float d2 = (s0 + s1) + (s2 + s3);
+              const float outv = a.squared ? d2 : sqrtf(d2);
+              dsum += (double)outv;
+              if (a.min_out) reinterpret_cast<float*>(a.min_out)[tile * BM + rr] = outv;
             }
+            rr = head[256 + rr];
           }
-          ++cnt;
-          rr = head[256 + rr];
+        }
+        __syncwarp();
+        if (wm == 0 && lane == 0) TRACE(13, it);
+        if (lane == 0) {
+          mbar_arrive(BAR(BAR_M_EMPTY + slot));
+          mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
         }
       }
-      __syncwarp();
-      if (wm == 0 && lane == 0) TRACE(13, it);
-#if BKM_TRACE
-      if (wm == 0 && lane == 0 && blockIdx.x == 0 && it < 128) g_tc_trace[14 * 128 + (int)it] = witers;
-#endif
-      if (lane == 0) {
-        mbar_arrive(BAR(BAR_M_EMPTY + slot));
-        mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
+      if (MSTEP && c < a.k) {
+        float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d + (size_t)c * a.d;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i < a.d) g[i] = acc[i];
+        a.pcnt[(size_t)blockIdx.x * a.k + c] = cnt;
       }
     }
-    if (lane == 0) red_s[wm] = 0.0;
-    if (c < a.k) {
-      float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d + (size_t)c * a.d;
+    // per-CTA sum of the distances: fixed shuffle tree per warp, warps added in order at the end
 #pragma unroll
-      for (int i = 0; i < 64; ++i) if (i < a.d) g[i] = acc[i];
-      a.pcnt[(size_t)blockIdx.x * a.k + c] = cnt;
-    }
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) red_s[wm] = dsum;
   } else if (warp >= MW0 && !LANE_OWNS) {
     // =========================== distance + M-step warps ===========================
     // Warp wm owns the rows whose label c satisfies c % NMW == wm.  Lane l holds features l and l+32 of
@@ -988,28 +1021,35 @@ bool tc_supported(int d, int k, int dtype) {
 }
 
 static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {
-  const bool lane_owns = mstep && !want_dist;
+  const bool lane_owns = !(mstep && want_dist);
+  const bool has_m = mstep || want_dist;
   c->KB = (d + 31) / 32;
   c->KS = (d + 15) / 16;
   c->NP = (k + 15) / 16 * 16;
   if (c->NP <= 128) { c->NU0 = c->NP; c->NU1 = 0; c->U = 1; }
   else { c->NU0 = (c->NP / 2 + 15) / 16 * 16; c->NU1 = c->NP - c->NU0; c->U = c->NU1 > 0 ? 2 : 1; }
   const uint32_t bbytes = (uint32_t)c->NP * 128u;               // one fp16 B tile: NP rows x 64 halves
-  // Pure Lloyd variant: 2 A stages (load -> convert) + 2 whole-tile M slots for the lane-owns-cluster M-step.
-  // Distance variants: direct mode (the M-step warps read the A ring) when >= 4 stages fit, which covers
-  // load -> convert -> MMA -> epilogue -> M-step; otherwise 2-3 stages plus a quarter-tile M ring.
-  for (int direct = lane_owns ? 0 : 1; direct >= 0; --direct) {
-    const int mr = lane_owns ? BM : MH;
-    for (int nst = direct ? NSTMAX : (lane_owns ? 2 : 3); nst >= (direct ? 4 : 2); --nst) {
+  // Shared-memory plans, tried in order:
+  //  lane-owns-cluster variants: 2 A stages (load -> convert) + 2 whole-tile M slots; labels only: A ring alone
+  //  sums + distances in one pass: direct mode (the M-step warps read the A ring) when >= 4 stages fit, which
+  //  covers load -> convert -> MMA -> epilogue -> M-step; otherwise 2-3 stages plus a quarter-tile M ring.
+  struct Plan { int direct, mring, mr, nst_hi, nst_lo; };
+  Plan plans[2];
+  int nplans = 0;
+  if (lane_owns) plans[nplans++] = has_m ? Plan{0, 1, BM, 2, 2} : Plan{0, 0, BM, 4, 2};
+  else { plans[nplans++] = Plan{1, 0, MH, NSTMAX, 4}; plans[nplans++] = Plan{0, 1, MH, 3, 2}; }
+  for (int pi = 0; pi < nplans; ++pi) {
+    const Plan& P = plans[pi];
+    for (int nst = P.nst_hi; nst >= P.nst_lo; --nst) {
       uint32_t o = 0;
       c->off_bhi = o; o += bbytes;
       c->off_blo = o; o += bbytes;
       c->off_bcn = o; o += (uint32_t)c->NP * 32u;                  // ||c||^2 operand tile
       c->off_ones = o; o += BM * 32u;                              // constant [1,1,1,0..] A tile
-      c->off_c32 = o; if (want_dist) o += (uint32_t)c->NP * c->KB * 128u;   // fp32 centres (distance variants)
+      c->off_c32 = o; if (!lane_owns) o += (uint32_t)c->NP * c->KB * 128u;   // fp32 centres (sums + distances variant)
       o = (uint32_t)align_up(o, 1024);
       c->off_x = o; o += (uint32_t)nst * c->KB * KBLK_BYTES;       // A ring
-      c->off_m = o; if (!direct) o += 2u * c->KB * mr * 128u;      // M ring
+      c->off_m = o; if (P.mring) o += 2u * c->KB * P.mr * 128u;    // M ring
       c->off_lab = o; o += NLAB * (lane_owns ? LIST_BYTES : BM * 4);   // per-cluster row lists / label buffers
       c->off_xn = o; o += 8 * BM * 4;                              // ||s x||^2 of the last 8 tiles (converter -> epilogue)
       c->off_red = o; o += (NMW + 1) * 8;
@@ -1017,8 +1057,9 @@ static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {
       c->off_tptr = o; o += 16;
       c->total = o;
       c->NST = nst;
-      c->direct = direct;
-      c->MR = mr;
+      c->direct = P.direct;
+      c->mring = P.mring;
+      c->MR = P.mr;
       if (o <= 227 * 1024) return true;
     }
   }
@@ -1027,7 +1068,7 @@ static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {
 
 int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
-  const bool want_dist = !mstep || a.min_out != nullptr || a.want_sum;
+  const bool want_dist = a.min_out != nullptr || a.want_sum;
   TcCfg cfg;
   if (!make_cfg(a.d, a.k, mstep, want_dist, &cfg)) return BKM_EUNSUPPORTED;
   CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
@@ -1051,7 +1092,7 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
     tc_chunk_kernel<M, W><<<grid, tc_threads(M, W), cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);                  \
   }
   if (mstep) { if (want_dist) TC_LAUNCH(true, true) else TC_LAUNCH(true, false) }
-  else TC_LAUNCH(false, true)
+  else { if (want_dist) TC_LAUNCH(false, true) else TC_LAUNCH(false, false) }
 #undef TC_LAUNCH
   note_launch(2);
   BKM_CUDA_TRY(cudaGetLastError());

@@ -235,6 +235,22 @@ def test_tcgen05_pipeline_tails(be, n, d, k, want_dist):
     assert torch.equal(counts, torch.bincount(got, minlength=k))
     ref = torch.zeros((k, d), dtype=torch.float64, device=be.device).index_add_(0, got, X.double())
     assert float((sums.view(k, d) - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) + 1e-9
+    # the assignment-only kernels (labels only / labels + distances) must agree with the Lloyd pass
+    lab2 = be.empty((n,), torch.int32)
+    if want_dist:
+        md = be.empty((n,), torch.float32)
+        ds = be.zeros((1,), torch.float64)
+        be.assign_chunk(X, pack, k, lab2, md, True, ds)
+        torch.cuda.synchronize()
+        exact = ((X.double() - C[lab2.long()]) ** 2).sum(1)
+        scale = (X.double() ** 2).sum(1) + (C ** 2).sum(1).max()       # fp32 centres: error relative to the norms
+        assert float(((md.double() - exact).abs() / scale).max()) < 2e-6
+        assert abs(float(ds[0]) - float(exact.sum())) <= 1e-5 * float(exact.sum()) + 2e-6 * float(scale.sum())
+    else:
+        be.assign_chunk(X, pack, k, lab2, None, True, None)
+        torch.cuda.synchronize()
+    assert be.lib.bkm_debug_abort_code() == 0
+    assert torch.equal(lab2, labels)
 
 
 def test_tcgen05_out_of_range_and_mixed_scales(be):
