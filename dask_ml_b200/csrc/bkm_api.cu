@@ -130,7 +130,9 @@ int bkm_kernel_family(int d, int k, int x_dtype, int flags) {
   bool tc = tc_supported(d, k, x_dtype);
   if (flags & BKM_FLAG_FORCE_SIMT) return 0;
   if (flags & BKM_FLAG_FORCE_TC) return tc ? 1 : BKM_EUNSUPPORTED;
-  return tc ? 1 : 0;
+  // The tensor kernel costs ~20 ns per row and SM whatever k and d are (per-tile pipeline costs), the
+  // CUDA-core kernel ~11 + 0.017 k d (measured, r01): tiny problems (C4: d=13, k=20) stay on the CUDA cores.
+  return (tc && (long long)k * d >= 512) ? 1 : 0;
 }
 
 int bkm_centers_pack_bytes(int k, int d, int x_dtype, size_t* out) {

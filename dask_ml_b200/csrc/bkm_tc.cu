@@ -1,6 +1,6 @@
 // bkm_tc.cu — fused E+M chunk kernel on the 5th-gen tensor cores (tcgen05 / TMEM / TMA), sm_100a.
 //
-// Shapes: fp32 X with d % 4 == 0, d <= 64, k <= 256 (BASELINE config C2: 10M x 64, k = 256).
+// Shapes: fp32 X with d <= 64 and a 16-byte aligned row pitch, k <= 256 (BASELINE config C2: 10M x 64, k = 256).
 //
 // Per 128-row tile of X the kernel computes  acc = s^2 ||c||^2 + (s X) . (-2 s C)^T  with the product as a
 // split-fp16 triple on the kind::f16 tensor pipe (twice the TF32 rate):
@@ -1017,7 +1017,10 @@ int tc_trace(long long* out, int n) {
 void tc_abort_detail(unsigned int* out64) { cudaMemcpyFromSymbol(out64, g_tc_dbg, 64 * sizeof(unsigned int)); }
 
 bool tc_supported(int d, int k, int dtype) {
-  return dtype == BKM_F32 && d >= 4 && d <= 64 && (d % 4) == 0 && k >= 1 && k <= 256;
+  // any d <= 64: columns beyond d are zero-filled by TMA; what TMA does need is a 16-byte row pitch and base
+  // (launch_tc returns BKM_EALIGN otherwise and the caller falls back to the CUDA-core kernel), which the host
+  // side provides by uploading row chunks with a padded pitch (engine.CudaBackend.to_device)
+  return dtype == BKM_F32 && d >= 1 && d <= 64 && k >= 1 && k <= 256;
 }
 
 static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {

@@ -120,6 +120,13 @@ class CudaBackend(object):
                 a = a.copy()                 # torch refuses read-only buffers
             t = torch.from_numpy(a)
         t = t.to(device=self.device, dtype=dtype, non_blocking=True)
+        if t.dim() == 2 and dtype == torch.float32 and t.shape[1] % 4 and t.shape[1] <= 64 and t.shape[0] > 0:
+            # The tensor path reads row tiles with TMA, which needs a 16-byte row pitch: rows are stored with the
+            # pitch rounded up to 4 floats (zero padded) and handed on as a (n, d) view of that buffer.
+            n, d = t.shape
+            buf = torch.zeros((n, (d + 3) // 4 * 4), dtype=dtype, device=self.device)
+            buf[:, :d] = t
+            return buf[:, :d]
         return t.contiguous()
 
     def empty(self, shape, dtype):

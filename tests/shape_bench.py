@@ -22,7 +22,7 @@ for name, n, d, k, dt in [("C3 KDD-shaped 4.9M x 41 f32 k=100", 4_898_431, 41, 1
                           ("C1 100k x 16 f64 k=8", 100_000, 16, 8, torch.float64),
                           ("C2 on the CUDA-core kernel (FORCE_SIMT) 2M x 64 f32 k=256", 2_000_000, 64, 256, torch.float32)]:
     be.flags = 1 if name.startswith("C2") else 0
-    X = synth_blobs_device(n, d, k, 7, be.device, dt)
+    X = be.to_device(synth_blobs_device(n, d, k, 7, be.device, dt), dt)      # padded row pitch when d % 4 != 0
     data = DeviceData([X], be, Comm())
     st = LloydState(data, X[:k].cpu().numpy().astype(np.float64))
     for _ in range(3):
@@ -38,7 +38,8 @@ for name, n, d, k, dt in [("C3 KDD-shaped 4.9M x 41 f32 k=100", 4_898_431, 41, 1
     s = 4 if dt == torch.float32 else 8
     gbs = n * (d * s + 4) / (ms * 1e-3) / 1e9
     tf = 2.0 * n * d * k / (ms * 1e-3) / 1e12
-    rec = {"shape": name, "kernel_family": int(be.kernel_family(d, k, dt)), "ms_per_iter": ms,
+    fam = int(be.kernel_family(d, k, dt)) if X.stride(0) % 4 == 0 else 0
+    rec = {"shape": name, "kernel_family": fam, "row_pitch": int(X.stride(0)), "ms_per_iter": ms,
            "samples_per_s": n / (ms * 1e-3), "hbm_gbs": gbs, "hbm_frac_of_measured": gbs / peaks["hbm_gbs"], "tflops": tf}
     print(json.dumps(rec), flush=True)
     del X, data, st

@@ -204,8 +204,7 @@ def _exact_labels_f64(x, C):
 def test_tcgen05_pipeline_tails(be, n, d, k, want_dist):
     import torch
 
-    if be.kernel_family(d, k, torch.float32) != 1:
-        pytest.skip("shape not on the tensor path")
+    be.flags = 2          # FORCE_TC: also the shapes the dispatcher would leave to the CUDA cores (k d < 512)
     g = torch.Generator(device=be.device).manual_seed(n + d + k)
     cent = torch.empty((max(2, k // 2), d), device=be.device).uniform_(-10, 10, generator=g)
     X = cent[torch.randint(0, cent.shape[0], (n,), device=be.device, generator=g)] + \
@@ -249,6 +248,7 @@ def test_tcgen05_pipeline_tails(be, n, d, k, want_dist):
     else:
         be.assign_chunk(X, pack, k, lab2, None, True, None)
         torch.cuda.synchronize()
+    be.flags = 0
     assert be.lib.bkm_debug_abort_code() == 0
     assert torch.equal(lab2, labels)
 
@@ -282,3 +282,45 @@ def test_tcgen05_out_of_range_and_mixed_scales(be):
         xs = (X.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
         assert bool((margin[bad] <= 1e-9 * xs).all()), int(bad.sum())
     assert int(counts.sum()) == n
+
+
+@pytest.mark.parametrize("n", [1000, 300_001])
+@pytest.mark.parametrize("d,k", [(1, 3), (3, 5), (13, 20), (41, 100), (63, 256)])
+def test_tcgen05_odd_feature_counts(be, oracle, n, d, k):
+    """d not a multiple of 4 runs on the tensor path once the rows are uploaded with a padded pitch
+    (BASELINE configs C3: d=41, k=100 and C4: d=13, k=20)."""
+    import torch
+
+    X = _blobs(n, d, max(2, k // 2), 3, "float32")
+    x = be.to_device(X, torch.float32)
+    assert x.stride(0) % 4 == 0 and x.shape == (n, d)
+    C = torch.as_tensor(X[np.random.RandomState(2).choice(n, k, replace=False)].astype(np.float64)).to(be.device)
+    C += 0.01 * torch.randn(C.shape, dtype=torch.float64, device=be.device, generator=torch.Generator(device=be.device).manual_seed(1))
+    be.flags = 2                      # FORCE_TC: fail instead of falling back to the CUDA-core kernel
+    try:
+        pack = be.pack_centers(C.contiguous(), torch.float32)
+        labels = be.empty((n,), torch.int32)
+        sums = be.zeros((k * d,), torch.float64)
+        counts = be.zeros((k,), torch.int64)
+        be.lloyd_chunk(x, pack, k, labels, None, sums, counts, None)
+        md = be.empty((n,), torch.float32)
+        ds = be.zeros((1,), torch.float64)
+        lab2 = be.empty((n,), torch.int32)
+        be.assign_chunk(x, pack, k, lab2, md, True, ds)
+        torch.cuda.synchronize()
+    finally:
+        be.flags = 0
+    assert be.lib.bkm_debug_abort_code() == 0
+    want, margin = _exact_labels_f64(x, C)
+    got = labels.long()
+    bad = got != want
+    if bool(bad.any()):
+        xs = (x.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
+        assert bool((margin[bad] <= 1e-9 * xs).all()), int(bad.sum())
+    assert torch.equal(lab2, labels)
+    assert torch.equal(counts, torch.bincount(got, minlength=k))
+    ref = torch.zeros((k, d), dtype=torch.float64, device=be.device).index_add_(0, got, x.double())
+    assert float((sums.view(k, d) - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) + 1e-9
+    exact = ((x.double() - C[got]) ** 2).sum(1)
+    scale = (x.double() ** 2).sum(1) + (C ** 2).sum(1).max()
+    assert float(((md.double() - exact).abs() / scale).max()) < 2e-6

@@ -40,7 +40,11 @@ def test_library_exports_every_declared_symbol():
     assert lib.bkm_workspace_bytes(1000, 64, 256, 0, ctypes.byref(out)) == 0 and out.value > 0
     assert lib.bkm_workspace_bytes(1000, 64, 256, 7, ctypes.byref(out)) == -2          # BKM_EDTYPE
     assert lib.bkm_kernel_family(64, 256, 0, 0) == 1      # tcgen05 path
-    assert lib.bkm_kernel_family(41, 100, 0, 0) == 0      # CUDA-core path (row pitch not 16-byte aligned)
+    assert lib.bkm_kernel_family(41, 100, 0, 0) == 1      # tcgen05 too (given a 16-byte row pitch; else the launch falls back)
+    assert lib.bkm_kernel_family(100, 100, 0, 0) == 0     # CUDA-core path: d > 64
+    assert lib.bkm_kernel_family(13, 20, 0, 0) == 0       # CUDA-core path: tiny k*d (per-tile costs of the tensor pipeline)
+    assert lib.bkm_kernel_family(13, 20, 0, 2) == 1       # ... unless forced
+    assert lib.bkm_kernel_family(64, 300, 0, 0) == 0      # CUDA-core path: k > 256
     assert lib.bkm_kernel_family(64, 256, 1, 0) == 0      # float64 -> CUDA cores
     assert lib.bkm_kernel_family(64, 1024, 0, 2) == -3    # FORCE_TC on an unsupported shape
 
