@@ -116,7 +116,11 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   __syncthreads();
 
   const long long ntiles = (a.n + TILE - 1) / TILE;
-  const bool flat_ok = (a.ldx == d) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  // rows with a small padding (the 16-byte pitch the tensor path wants, e.g. 13 -> 16) are streamed like
+  // contiguous ones: the whole [rows][ldx] block is read with 16-byte loads and the padding is dropped
+  const int L = (int)a.ldx;
+  const bool flat_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                       (a.ldx == d || (a.ldx <= d + 8 && (a.ldx * sizeof(T)) % 16 == 0));
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long r0 = tile * TILE;
@@ -125,8 +129,8 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
     // ---- stage the tile: coalesced loads, [row][pitch] layout in smem ----
     if (flat_ok) {
       const int per16 = 16 / (int)sizeof(T);
-      const long long nelem = (long long)rows * d;
-      const T* src = X + r0 * (long long)d;     // 16-byte aligned: r0 is a multiple of TILE
+      const long long nelem = (long long)rows * L;
+      const T* src = X + r0 * (long long)L;     // 16-byte aligned: r0 is a multiple of TILE
       const long long nvec = nelem / per16;
       for (long long v = tid; v < nvec; v += TILE) {
         T e[4];
@@ -138,18 +142,18 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
           e[0] = (T)t.x; e[1] = (T)t.y;
         }
         long long e0 = v * per16;
-        int row = (int)(e0 / d);
-        int col = (int)(e0 - (long long)row * d);
+        int row = (int)(e0 / L);
+        int col = (int)(e0 - (long long)row * L);
 #pragma unroll
         for (int q = 0; q < per16; ++q) {
-          xs[row * pitch + col] = e[q];
-          if (++col == d) { col = 0; ++row; }
+          if (col < d) xs[row * pitch + col] = e[q];
+          if (++col == L) { col = 0; ++row; }
         }
       }
       for (long long e0 = nvec * per16 + tid; e0 < nelem; e0 += TILE) {
-        int row = (int)(e0 / d);
-        int col = (int)(e0 - (long long)row * d);
-        xs[row * pitch + col] = src[e0];
+        int row = (int)(e0 / L);
+        int col = (int)(e0 - (long long)row * L);
+        if (col < d) xs[row * pitch + col] = src[e0];
       }
     } else {
       for (int r = warp; r < rows; r += NW) {
