@@ -57,6 +57,8 @@ struct TcCfg {
   int NST;       // X stages
   int direct;    // 1: the (warp-owns-clusters) M-step warps read the A ring
   int mring;     // 1: separate M ring (quarter-tile or whole-tile slots)
+  int SSH;       // lane-owns flavour: every cluster has 2^SSH row lists (rows r with the same r mod 2^SSH), one lane each,
+                 // so that k < 256 still uses all 256 lanes: 2^SSH = 256 / next_pow2(k)
   int MR;        // rows per M-ring slot (32: quarter tiles, 128: whole tiles)
   uint32_t off_bhi, off_blo, off_bcn, off_ones, off_c32, off_x, off_m, off_lab, off_xn, off_red, off_bar, off_tptr, total;
 };
@@ -634,7 +636,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         if (LANE_OWNS) {
           // push the row onto its cluster's list (the owner lane of the M-step warps walks it)
           int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
-          if (valid && !flagged) head[256 + r] = atomicExch(&head[bj], r);
+          if (valid && !flagged) head[256 + r] = atomicExch(&head[(bj << cfg.SSH) | (r & ((1 << cfg.SSH) - 1))], r);
         } else {
           lab_s[lb * BM + r] = (valid && !flagged) ? bj : -1;
         }
@@ -654,7 +656,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     // row & 7 hit different banks).  No cross-lane traffic, no selection of an accumulator at run time,
     // and 64 independent adds per row instead of a dependent chain per row.
     const int wm = warp - MW0;
-    const int c = wm * 32 + lane;
+    const int v = wm * 32 + lane;            // list index: (cluster << SSH) | (row mod 2^SSH)
+    const int c = v >> cfg.SSH;              // this lane's cluster
     double dsum = 0.0;
     if (HAS_M) {
       // MSTEP: the running sums of cluster c.  Distance variant: the fp32 centre c itself, so that the winning
@@ -680,8 +683,8 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         if (wm == 0 && lane == 0) TRACE(12, it);
         int* head = reinterpret_cast<int*>(smem + cfg.off_lab + lb * LIST_BYTES);
         const unsigned char* xs = smem + cfg.off_m + slot * stage_bytes;      // full-tile slot: same layout as an A stage
-        int rr = head[c];
-        head[c] = -1;
+        int rr = head[v];
+        head[v] = -1;
         int guard = BM;                                 // a list holds at most the tile's rows (a corrupted list must not spin)
 #pragma unroll 1
         while (__any_sync(0xffffffffu, rr >= 0) && guard-- > 0) {
@@ -735,11 +738,19 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
           mbar_arrive(BAR(BAR_LAB_EMPTY + lb));
         }
       }
-      if (MSTEP && c < a.k) {
-        float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d + (size_t)c * a.d;
+      if (MSTEP) {
+        // the 2^SSH lanes of a cluster are adjacent: fold them (fixed shuffle tree), the first one writes
+        for (int o = (1 << cfg.SSH) >> 1; o > 0; o >>= 1) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i < a.d) g[i] = acc[i];
-        a.pcnt[(size_t)blockIdx.x * a.k + c] = cnt;
+          for (int i = 0; i < 64; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+          cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (c < a.k && (v & ((1 << cfg.SSH) - 1)) == 0) {
+          float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * a.k * a.d + (size_t)c * a.d;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (i < a.d) g[i] = acc[i];
+          a.pcnt[(size_t)blockIdx.x * a.k + c] = cnt;
+        }
       }
     }
     // per-CTA sum of the distances: fixed shuffle tree per warp, warps added in order at the end
@@ -1063,6 +1074,8 @@ static bool make_cfg(int d, int k, bool mstep, bool want_dist, TcCfg* c) {
       c->direct = P.direct;
       c->mring = P.mring;
       c->MR = P.mr;
+      c->SSH = 0;
+      if (lane_owns) { int p2 = 1; while (p2 < k) p2 <<= 1; while ((p2 << c->SSH) < 256 && c->SSH < 5) ++c->SSH; }   // <= one warp per cluster
       if (o <= 227 * 1024) return true;
     }
   }

@@ -1,6 +1,6 @@
 """Manual pipeline-timeline probe (not collected by pytest).  Needs a `make -C dask_ml_b200/csrc TRACE=1`
 build: prints, for CTA 0, when each pipeline role reached each event of tiles [lo, hi) in SM cycles.
-Run on the GPU box:  python tests/tc_trace.py [lo hi] [want_dist]"""
+Run on the GPU box:  python tests/tc_trace.py [lo hi] [dist|lloyd] [d k]"""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,12 +10,14 @@ from dask_ml_b200 import _lib
 
 lo = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 hi = int(sys.argv[2]) if len(sys.argv) > 2 else 52
-want_dist = len(sys.argv) > 3
+want_dist = len(sys.argv) > 3 and sys.argv[3] == "dist"
 be = CudaBackend(flags=_lib.FLAG_FORCE_TC)
-n, d, k = 148 * 128 * 128, 64, 256
+d = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+k = int(sys.argv[5]) if len(sys.argv) > 5 else 256
+n = 148 * 128 * 128
 g = torch.Generator(device="cuda").manual_seed(0)
 cent = torch.empty((k, d), device="cuda").uniform_(-10, 10, generator=g)
-X = cent[torch.randint(0, k, (n,), device="cuda", generator=g)] + torch.randn((n, d), device="cuda", generator=g)
+X = be.to_device(cent[torch.randint(0, k, (n,), device="cuda", generator=g)] + torch.randn((n, d), device="cuda", generator=g), torch.float32)
 C = X[torch.randperm(n, device="cuda", generator=g)[:k]].double()
 pack = be.pack_centers(C, torch.float32)
 labels = be.empty((n,), torch.int32)
