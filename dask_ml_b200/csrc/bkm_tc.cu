@@ -11,20 +11,24 @@
 // dask_ml/metrics/pairwise.py:35-38) except on near-ties, which are re-decided in float64 (as are rows whose
 // scaled entries leave fp16's range).  ||c||^2 enters through one extra tf32 K-step (rows [hi,mid,lo,0..]
 // against a constant [1,1,1,0..] tile).  The M-step (_centers_dense, dask_ml/cluster/k_means.py:572-582) is
-// fused: rows are scatter-added into REGISTER-resident per-CTA sums, X is read from HBM once.
+// fused: rows are added into REGISTER-resident per-CTA sums, X is read from HBM once.
 //
-// Warp roles (896 threads):
-//   0       TMA producer of the A ring (NST x 128-row fp32 X tiles, SWIZZLE_128B) + L2 prefetch ahead
-//   1       MMA issuer (warp-converged, uniform-register operands, one elected lane issues tcgen05.mma/commit)
-//   2       TMEM allocator (512 columns: 3 x 128 accumulator buffers + 2 x (32 Xhi + 32 Xlo))
-//   3       [ring mode only] TMA producer of the M ring (32-row quarter tiles re-fetched from L2)
-//   4-7, 8-11   two converter + epilogue warp sets on alternate tiles (thread == row == TMEM lane)
-//   12-27   16 distance + M-step warps (warp w owns clusters c % 16 == w; lane l holds features l, l+32)
-// The M-step warps read the rows either straight from the A ring (direct mode: the ring is >= 4 stages deep,
-// a stage is released by the converter set AND the 16 M-step warps) or, when shared memory is short (the
-// distance variants keep an fp32 copy of the centres), from a small separate ring.
-// Pipelines (mbarriers): A ring full/empty, accumulator full/empty per (epilogue set, buffer), X operands
-// in TMEM full, labels full/empty, M ring full/empty.  DESIGN.md has the full description.
+// Warp roles (768 threads; roles are assigned per aligned warpgroup, setmaxnreg moves registers between them):
+//   0       TMA producer: polls the A ring (2-4 x 128-row fp32 X tiles, SWIZZLE_128B, L2 prefetch ahead) and the
+//           M ring (the same tiles re-fetched from L2 for the M-step / distance warps); allocates TMEM
+//   1, 2    MMA issuers on alternate accumulator units (warp-converged, uniform-register operands, one elected lane
+//           issues tcgen05.mma / commit); 3 spare
+//   4-7     converter: s X -> fp16 (hi, lo) pairs -> TMEM operand slot, ||s x||^2 -> shared memory; runs ahead
+//   8-11, 12-15   two epilogue sets on alternate tiles (thread == row == TMEM lane), single pass over the accumulator
+//   16-23   M-step / distance warps, lane-owns-cluster flavour: lane j of warp w walks the row lists of cluster
+//           32w+j that the epilogue linked, keeping the cluster's sums (Lloyd step) or centre (distances) in
+//           registers.  The <MSTEP, WANT_DIST> = <true, true> variant keeps the older flavour instead (16 warps,
+//           warp w owns clusters c % 16 == w, lane l holds features l, l+32, fp32 centres in shared memory).
+// TMEM (512 columns): 3 x 128 accumulator buffers + 2 x (32 Xhi + 32 Xlo) operand columns.
+// Pipelines (mbarriers): A ring full/empty, M ring full/empty, operands ready (8 deep) / operand slot free,
+// accumulator full per (epilogue set, buffer) / empty per (set, buffer, issuer), labels full/empty.
+// Every barrier has one kind of waiter that sees consecutive phases: a parity wait asked before the previous
+// phase or after the next one has completed would succeed spuriously / never return.  DESIGN.md has the rest.
 #include "bkm_common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>

@@ -1,4 +1,4 @@
-"""Manual probe of the tcgen05 path (not collected by pytest): accuracy of the 3xTF32 product and parity
+"""Manual probe of the tcgen05 path (not collected by pytest): accuracy of the split-fp16 product and parity
 with the oracle on a few shapes.  Run on the GPU box:  python tests/tc_probe.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
