@@ -37,9 +37,13 @@ static int sm_count_of_current(int* out) {
 static float tau_for(int d, int dtype, int flags, int family) {
   if (dtype != BKM_F32 || (flags & BKM_FLAG_NO_RECHECK)) return 0.f;
   const float eps = 1.0f / 16777216.0f;   // 2^-24
-  // tcgen05 path: 3*ceil(d/8) accumulations into an fp32 TMEM accumulator of magnitude ~(||x||^2+||c||^2)
-  // plus the dropped lo*lo term of the 3xTF32 split (2^-21); measured worst margin of a flipped label on
-  // blobs data: 3.6e-7 -> the bound below (3.3e-6 at d=64) leaves ~9x headroom.
+  // tcgen05 path (split-fp16 triple, scaled by a power of two): error sources relative to ||x||^2+||c||^2 are the
+  // fp16 (hi, lo) representation of both operands (2^-22 each; 2^-25 absolute in scaled units when lo falls into
+  // fp16's subnormals, negligible because the scale puts max|c| at 2^9..2^10), the dropped lo*lo term (2^-24),
+  // the 3*ceil(d/16)+1 accumulations into the fp32 TMEM accumulator, and the accumulator's own rounding.
+  // Measured worst margin of a label that differs from float64 on blobs data: 3.6e-7; the bound below
+  // (3.3e-6 at d=64) leaves ~9x headroom, and the parity tests assert that every remaining difference is a
+  // float64 near-tie (margin <= 1e-9 relative).
   if (family == 1) return (8.0f * sqrtf(3.0f * (float)((d + 7) / 8)) + 16.0f) * eps;
   return 8.0f * (sqrtf((float)d) + 2.0f) * eps;
 }
