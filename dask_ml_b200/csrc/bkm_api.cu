@@ -41,9 +41,9 @@ static float tau_for(int d, int dtype, int flags, int family) {
   // fp16 (hi, lo) representation of both operands (2^-22 each; 2^-25 absolute in scaled units when lo falls into
   // fp16's subnormals, negligible because the scale puts max|c| at 2^9..2^10), the dropped lo*lo term (2^-24),
   // the 3*ceil(d/16)+1 accumulations into the fp32 TMEM accumulator, and the accumulator's own rounding.
-  // Measured worst margin of a label that differs from float64 on blobs data: 3.6e-7; the bound below
-  // (3.3e-6 at d=64) leaves ~9x headroom, and the parity tests assert that every remaining difference is a
-  // float64 near-tie (margin <= 1e-9 relative).
+  // Measured with the re-check switched off (tests/tau_probe.py, 14M rows of blobs / uniform / badly scaled data):
+  // worst margin of a label that differs from float64 = 4.8e-7; the bound below (3.3e-6 at d=64) leaves ~7x
+  // headroom, and the parity tests assert that every remaining difference is a float64 near-tie (<= 1e-9).
   if (family == 1) return (8.0f * sqrtf(3.0f * (float)((d + 7) / 8)) + 16.0f) * eps;
   return 8.0f * (sqrtf((float)d) + 2.0f) * eps;
 }
