@@ -900,6 +900,13 @@ tc_recheck_kernel(ChunkArgs a, bool mstep, double* sums, unsigned long long* cou
   __shared__ double wd[RCK_ROWS][8];
   __shared__ int wj[RCK_ROWS][8];
   __shared__ long long rows_s[RCK_ROWS];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)&g_tc_abort) {
+    // a pipeline wait of the fused kernel timed out (see mbar_wait): its outputs are garbage.  Make that loud:
+    // NaN sums / cost and a negative label instead of plausible numbers (bkm_debug_abort_code tells which wait).
+    if (mstep && sums) sums[0] = CUDART_NAN;
+    if (dist_sum) *dist_sum = CUDART_NAN;
+    if (a.labels && a.n > 0) a.labels[0] = -1;
+  }
   const int cnt = *a.defer_cnt;
   if ((int)blockIdx.x * RCK_ROWS >= cnt) return;
   const int k = a.k, d = a.d, tid = threadIdx.x, kp = a.L.kp, lane = tid & 31, wid = tid >> 5;
