@@ -93,14 +93,15 @@ class CudaBackend(object):
 
     def _workspace(self, n, d, k, dtype):
         """Scratch for one chunk call (per-CTA partials + the deferred-row list, 4 bytes per row)."""
-        key = (d, k, dtype)
-        ws = self._ws.get(key)
+        # one grow-only buffer for every shape: the layout inside it is recomputed by the library per call, and
+        # k-means|| changes k every round (a buffer per k would allocate ~100 MB per round and keep them all)
+        ws = self._ws.get("buf")
         nbytes = ctypes.c_size_t(0)
         _lib.check(self.lib.bkm_workspace_bytes(int(n), d, k, _DT_CODE[dtype], ctypes.byref(nbytes)),
                    "bkm_workspace_bytes")
         if ws is None or ws.numel() < nbytes.value:
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
-            self._ws[key] = ws
+            ws = torch.empty(int(nbytes.value * 1.25) + (1 << 20), dtype=torch.uint8, device=self.device)
+            self._ws["buf"] = ws
         return ws
 
     def kernel_family(self, d, k, dtype):
