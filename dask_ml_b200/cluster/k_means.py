@@ -367,11 +367,26 @@ def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_
     if max_iter is not None:
         n_iter = min(max_iter, n_iter)
 
-    # Steps 3-6: oversampling rounds (k_means.py:423-435)
+    # Steps 3-6: oversampling rounds (k_means.py:423-435).  The reference re-evaluates the distances to ALL
+    # candidates every round; min_j d(x, c_j) over a growing set is the running minimum of the per-round minima, so
+    # each round only sweeps the candidates that are new (in blocks of <= 256: the tensor path's limit) and folds
+    # them into the per-chunk running minimum kept on the device.
+    run_min = None
+    swept = set()
     for i in range(n_iter):
         with _timer("init iteration %2d/%2d , %2d centers" % (i + 1, n_iter, len(c_idx)), _logger=logger):
             seed = int(rs.randint(0, 2 ** 31 - 1)) | (int(rs.randint(0, 2 ** 31 - 1)) << 32)
-            _, mins, phi_t = sweep.run(centers.astype(np.float64), want_min=True, squared=True)
+            fresh = sorted(c_idx - swept)
+            for b0 in range(0, len(fresh), 256):
+                block = X.global_rows(fresh[b0:b0 + 256]).astype(np.float64)
+                _, mins_b, _ = sweep.run(block, want_min=True, squared=True)
+                run_min = mins_b if run_min is None else [torch.minimum(a, b) for a, b in zip(run_min, mins_b)]
+            swept |= set(fresh)
+            mins = run_min
+            phi_t = be.zeros((1,), torch.float64)
+            for mn in mins:
+                phi_t += mn.sum(dtype=torch.float64)
+            comm.allreduce_sum_(phi_t)
             phi = float(phi_t.item())
             new_idxs = set()
             if phi > 0:
@@ -391,8 +406,8 @@ def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_
                 for part in comm.allgather_obj(local):
                     new_idxs |= set(int(v) for v in part)
             c_idx |= new_idxs
-        # sorted, like the reference (k_means.py:432-435)
-        centers = X.global_rows(sorted(c_idx))
+    # sorted, like the reference (k_means.py:432-435); fetched once, after the last round
+    centers = X.global_rows(sorted(c_idx))
 
     if len(centers) < n_clusters:
         logger.warning("Found fewer than %d clusters in init.", n_clusters)

@@ -224,8 +224,11 @@ class DeviceData(object):
         local_idx = np.asarray(local_idx, dtype=np.int64)
         out = np.empty((len(local_idx), self.d), dtype=self.np_dtype)
         which = np.searchsorted(self.chunk_offsets, local_idx, side="right") - 1
-        for p, (i, w) in enumerate(zip(local_idx, which)):
-            out[p] = self.chunks[w][int(i - self.chunk_offsets[w])].cpu().numpy()
+        # one gather + one device-to-host copy per chunk that holds requested rows (not one copy per row)
+        for w in np.unique(which):
+            pos = np.nonzero(which == w)[0]
+            rel = torch.as_tensor(local_idx[pos] - self.chunk_offsets[w], dtype=torch.int64, device=self.chunks[w].device)
+            out[pos] = self.chunks[w].index_select(0, rel).cpu().numpy()
         return out
 
     def global_rows(self, global_idx):
