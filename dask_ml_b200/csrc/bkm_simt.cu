@@ -113,6 +113,14 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   for (int i = tid; i < TILE * pitch; i += TILE) xs[i] = T(0);
   const T cnmax = (T)hdr->cn_max;
   double inertia_acc = 0.0;
+  // Few clusters (k <= 32, d <= 16; BASELINE C4 / C1): lane j of every warp owns cluster j and keeps the sums of the
+  // rows of ITS warp's 32-row slice in registers — lanes work on different rows at the same time, where the general
+  // M-step below walks the rows one by one.  Folded into the shared-memory sums once, at the end of the kernel.
+  const bool smallk = MSTEP && !GLOBAL && k <= 32 && d <= 16;
+  PS lacc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) lacc[i] = PS(0);
+  int lcnt = 0;
   __syncthreads();
 
   const long long ntiles = (a.n + TILE - 1) / TILE;
@@ -274,7 +282,22 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
     }
 
     // ---- M-step: warp w owns clusters c with c % NW == w; no atomics in SMEM mode ----
-    if (MSTEP) {
+    if (MSTEP && smallk) {
+      const int rbase = warp * 32;
+      const int ml = (rbase + lane < rows) ? lab_s[rbase + lane] : -1;
+      unsigned mine = 0;                                   // rows of this warp's slice that belong to cluster `lane`
+      for (int j = 0; j < k; ++j) {
+        const unsigned mj = __ballot_sync(0xffffffffu, ml == j);
+        if (lane == j) mine = mj;
+      }
+      while (mine) {
+        const int b = __ffs(mine) - 1; mine &= mine - 1;
+        const T* xr = xs + (rbase + b) * pitch;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < d) lacc[i] += (PS)xr[i];
+        ++lcnt;
+      }
+    } else if (MSTEP) {
       for (int base = 0; base < rows; base += 32) {
         int ml = (base + lane < rows) ? lab_s[base + lane] : -1;
         bool mine = GLOBAL ? (ml >= 0 && ((base >> 5) % NW) == warp) : (ml >= 0 && (ml % NW) == warp);
@@ -299,6 +322,17 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   }
 
   // ---- flush per-CTA partials ----
+  if (MSTEP && smallk) {
+    // warps add their lane-resident sums in warp order (fixed order: reproducible)
+    for (int w = 0; w < NW; ++w) {
+      if (warp == w && lane < k) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < d) sums_s[lane * d + i] += lacc[i];
+        cnts_s[lane] += lcnt;
+      }
+      __syncthreads();
+    }
+  }
   if (MSTEP) {
     if (!GLOBAL) {
       PS* g = reinterpret_cast<PS*>(a.psum) + (size_t)blockIdx.x * k * d;
