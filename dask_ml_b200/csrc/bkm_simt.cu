@@ -74,7 +74,7 @@ static inline SimtSmem simt_smem(int k, int d, int J, bool mstep, bool global_mo
   return S;
 }
 
-template <typename T, int J, bool MSTEP, bool GLOBAL>
+template <typename T, int J, bool MSTEP, bool GLOBAL, bool SMALLK>
 __global__ void __launch_bounds__(TILE)
 simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   typedef typename PsumT<T>::type PS;
@@ -116,10 +116,11 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   // Few clusters (k <= 32, d <= 16; BASELINE C4 / C1): lane j of every warp owns cluster j and keeps the sums of the
   // rows of ITS warp's 32-row slice in registers — lanes work on different rows at the same time, where the general
   // M-step below walks the rows one by one.  Folded into the shared-memory sums once, at the end of the kernel.
-  const bool smallk = MSTEP && !GLOBAL && k <= 32 && d <= 16;
-  PS lacc[16];
+  // (a separate instantiation, so that the general kernel does not carry the 16 accumulator registers)
+  constexpr bool smallk = SMALLK;
+  PS lacc[SMALLK ? 16 : 1];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) lacc[i] = PS(0);
+  for (int i = 0; i < (SMALLK ? 16 : 1); ++i) lacc[i] = PS(0);
   int lcnt = 0;
   __syncthreads();
 
@@ -294,7 +295,7 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
         const int b = __ffs(mine) - 1; mine &= mine - 1;
         const T* xr = xs + (rbase + b) * pitch;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < d) lacc[i] += (PS)xr[i];
+        for (int i = 0; i < (SMALLK ? 16 : 1); ++i) if (i < d) lacc[i] += (PS)xr[i];
         ++lcnt;
       }
     } else if (MSTEP) {
@@ -327,7 +328,7 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
     for (int w = 0; w < NW; ++w) {
       if (warp == w && lane < k) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < d) sums_s[lane * d + i] += lacc[i];
+        for (int i = 0; i < (SMALLK ? 16 : 1); ++i) if (i < d) sums_s[lane * d + i] += lacc[i];
         cnts_s[lane] += lcnt;
       }
       __syncthreads();
@@ -353,10 +354,10 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   }
 }
 
-template <typename T, int J, bool MSTEP, bool GLOBAL>
+template <typename T, int J, bool MSTEP, bool GLOBAL, bool SMALLK = false>
 static int launch_one(const ChunkArgs& a, int sm_count, int* grid_out, cudaStream_t s) {
   SimtSmem S = simt_smem<T>(a.k, a.d, J, MSTEP, GLOBAL);
-  auto kern = simt_chunk_kernel<T, J, MSTEP, GLOBAL>;
+  auto kern = simt_chunk_kernel<T, J, MSTEP, GLOBAL, SMALLK>;
   BKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
   int occ = 0;
   BKM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, S.total));
@@ -386,6 +387,7 @@ static int launch_T(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out,
 #define BKM_DISPATCH(JJ)                                                                   \
   if (mstep) {                                                                             \
     if (global_mode) return launch_one<T, JJ, true, true>(a, sm_count, grid_out, s);       \
+    if (k <= 32 && a.d <= 16) return launch_one<T, JJ, true, false, true>(a, sm_count, grid_out, s);   /* lane-owns-cluster M-step */ \
     return launch_one<T, JJ, true, false>(a, sm_count, grid_out, s);                       \
   } else {                                                                                 \
     if (global_mode) return launch_one<T, JJ, false, true>(a, sm_count, grid_out, s);      \
