@@ -4,21 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): synthetic blobs 10M x 64 float32, k = 256, one chunk per
-GPU, fixed init = first k rows.  A *step* is one full Lloyd iteration over the resident chunk:
-fused E+M kernel -> (N>1: one all-reduce of [k*d sums | k counts | inertia]) -> centre update + shift.
-With N>1 every rank holds its own 10M-row chunk (weak scaling, no data-path collective besides the
-per-iteration all-reduce).  Rank 0 prints ONE JSON line.
+Headline workload (BASELINE.json configs[1], "C2"): synthetic blobs 10M x 64 float32, k = 256, one chunk per GPU,
+fixed init = first k rows.  A *step* is one full Lloyd iteration as ``KMeans.fit`` runs it
+(``dask_ml_b200.cluster.k_means.lloyd_loop``): centre pack -> fused E+M kernel over the resident chunk -> (N>1: one
+all-reduce of [k*d sums | k counts | inertia]) -> centre update + shift -> ONE host read of the shift (the stop test,
+dask_ml/cluster/k_means.py:552-559).  With N>1 every rank holds its own 10M-row chunk (weak scaling).
+Rank 0 prints ONE JSON line.
 
 Numbers reported:
-  value        whole-job samples/s with X resident in HBM (CUDA events, max over ranks)
-  e2e          same metric through ``lloyd_iteration_host`` with X in pinned HOST memory: every step
-               copies X host->device (double-buffered row blocks) and reads the new centres back
-  roofline     the fused chunk kernel against the tensor (dense 16-bit) and HBM roofs, algorithmic work
-               2*d*k flops and d*4+4 bytes per sample
-  cpu_baseline the dask-ml path restated without dask (oracle/: scikit-learn E-step + C scatter-add,
-               thread pool over os.cpu_count() row blocks) on a bounded row sample of the same workload
-``--impl reference`` times only that CPU path and prints the same line shape.
+  value         whole-job samples/s with X resident in HBM (CUDA events around the K iterations, max over ranks)
+  e2e           same metric through ``lloyd_iteration_host`` with X in pinned HOST memory: every step copies X
+                host->device (double-buffered row blocks) and reads the new centres back
+  roofline      the fused chunk kernel against the tensor (dense 16-bit) and HBM roofs, algorithmic work 2*d*k flops and
+                d*4+4 bytes per sample
+  parity_check  labels of the LAST timed iteration on a >= 1M-row slice against the float64 arg-min evaluated on the
+                device (mismatches must be float64 near-ties; worst relative margin reported) + deferred-row fraction
+  configs       the other BASELINE shapes as sub-records, same loop, same parity check: C3 (4.9M x 41, k=100; with N>1
+                the SAME 4.9M rows are split across ranks = strong scaling), C4 (15M x 13, k=20 per GPU = the 8-GPU
+                shard of 120M x 13; weak), C5s (a slice of C5: bf16, d=128, k=1024) when the build supports it
+  allreduce_us  N>1: latency of the per-iteration collective on the [k*d+k+1] float64 buffer, CUDA events
+  cpu_baseline  the dask-ml path restated without dask (oracle/: scikit-learn float64 E-step + the reference's numba
+                scatter-add, thread pool over row blocks) on a bounded row sample of C2
+``--impl reference`` times that CPU path alone on the FULL 10M-row C2 chunk and prints the same line shape.
 """
 import argparse
 import json
@@ -38,10 +45,20 @@ os.environ.setdefault("MKL_NUM_THREADS", "1")
 
 import numpy as np  # noqa: E402
 
-N_ROWS = 10_000_000
-N_FEAT = 64
-N_CLUST = 256
 METRIC = "kmeans_lloyd_iter_samples_per_sec"
+
+# name -> rows (per GPU for weak configs, total for the strong one), features, clusters, input dtype, scaling
+CONFIGS = {
+    "C2": dict(n=10_000_000, d=64, k=256, dtype="f32", scaling="weak", gen="blobs", seed=0,
+               what="synthetic blobs 10M x 64 float32, k=256 (BASELINE configs[1])"),
+    "C3": dict(n=4_898_431, d=41, k=100, dtype="f32", scaling="strong", gen="kdd", seed=1,
+               what="KDD-Cup-99-shaped 4,898,431 x 41 float32, k=100 (benchmarks/k_means_kdd.py shape); N>1 splits the SAME rows"),
+    "C4": dict(n=15_000_000, d=13, k=20, dtype="f32", scaling="weak", gen="airline", seed=2,
+               what="airline-shaped 15M x 13 float32 per GPU, k=20 (the 8-GPU shard of 120M x 13, benchmarks/kmeans_airline.py shape)"),
+    "C5s": dict(n=8_000_000, d=128, k=1024, dtype="bf16", scaling="weak", gen="blobs", seed=3,
+                what="slice of C5: 8M x 128 bf16 per GPU, k=1024 (C5 is 125M rows per GPU; samples/s is linear in n)"),
+}
+N_ROWS, N_FEAT, N_CLUST = CONFIGS["C2"]["n"], CONFIGS["C2"]["d"], CONFIGS["C2"]["k"]
 
 
 def _peaks():
@@ -53,14 +70,10 @@ def _peaks():
     else:
         m = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
         src = "fallback"
-    t = os.path.join(ROOT, "profiles", "tf32_peak.json")
-    tf32 = None
-    if os.path.exists(t):
-        with open(t) as f:
-            tf32 = json.load(f)
-    return m, src, tf32
+    return m, src
 
 
+# ------------------------------------------------------------------------------------------ synthetic inputs
 def synth_blobs_device(n, d, k_true, seed, device, dtype):
     """k_true isotropic blobs, centres ~U(-10,10)^d, sigma=1, generated on the device in row blocks."""
     import torch
@@ -77,11 +90,51 @@ def synth_blobs_device(n, d, k_true, seed, device, dtype):
     return X
 
 
+def synth_config_device(name, n, seed, device):
+    """SURVEY.md §8(d) generators.  C3: 38 blob columns + 3 low-cardinality integer-coded columns (values 0..69) like the
+    coded categoricals of the KDD table; C4: 20 true centres, heterogeneous column scales 1 ... 1e3."""
+    import torch
+
+    cfg = CONFIGS[name]
+    d, k = cfg["d"], cfg["k"]
+    tdt = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
+    if cfg["gen"] == "blobs":
+        return synth_blobs_device(n, d, k, 1000 * cfg["seed"] + seed, device, tdt)
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 * cfg["seed"] + seed)
+    X = torch.empty((n, d), device=device, dtype=torch.float32)
+    blk = 1 << 20
+    if cfg["gen"] == "kdd":
+        cent = torch.rand((k, 38), generator=g, device=device) * 20.0 - 10.0
+        codes = torch.randint(0, 70, (k, 3), generator=g, device=device).float()
+        for s in range(0, n, blk):
+            m = min(blk, n - s)
+            idx = torch.randint(0, k, (m,), generator=g, device=device)
+            X[s:s + m, :38] = cent[idx] + torch.randn((m, 38), generator=g, device=device)
+            # the coded columns follow the row's cluster 90 % of the time, else a random code
+            rnd = torch.randint(0, 70, (m, 3), generator=g, device=device).float()
+            keep = torch.rand((m, 3), generator=g, device=device) < 0.9
+            X[s:s + m, 38:] = torch.where(keep, codes[idx], rnd)
+    else:   # airline
+        scales = torch.logspace(0, 3, d, device=device)
+        cent = (torch.rand((k, d), generator=g, device=device) * 20.0 - 10.0) * scales
+        for s in range(0, n, blk):
+            m = min(blk, n - s)
+            idx = torch.randint(0, k, (m,), generator=g, device=device)
+            X[s:s + m] = cent[idx] + torch.randn((m, d), generator=g, device=device) * scales
+    return X
+
+
 def synth_blobs_host(n, d, k_true, seed):
     rng = np.random.default_rng(seed)
     cent = rng.uniform(-10, 10, size=(k_true, d)).astype(np.float32)
-    idx = rng.integers(0, k_true, size=n)
-    return cent[idx] + rng.standard_normal((n, d), dtype=np.float32)
+    X = np.empty((n, d), dtype=np.float32)
+    blk = 1 << 20
+    for s in range(0, n, blk):
+        m = min(blk, n - s)
+        idx = rng.integers(0, k_true, size=m)
+        X[s:s + m] = cent[idx] + rng.standard_normal((m, d), dtype=np.float32)
+    return X
 
 
 class ClockSampler(threading.Thread):
@@ -115,7 +168,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.05)
+                time.sleep(0.02)
         except Exception as e:  # pragma: no cover
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
@@ -129,52 +182,224 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # CPU baseline (oracle) — the only place bench.py touches oracle/
 # ------------------------------------------------------------------------------------------
+def _cpu_versions():
+    import sklearn
+    import scipy
+
+    v = {"sklearn": sklearn.__version__, "numpy": np.__version__, "scipy": scipy.__version__}
+    try:
+        import numba
+
+        v["numba"] = numba.__version__
+    except Exception:
+        v["numba"] = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    v["cpu"] = line.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    return v
+
+
 def cpu_lloyd_baseline(sample_rows, iters, warm):
+    """The dask-ml Lloyd iteration restated without dask (oracle/kmeans_oracle.py: scikit-learn float64 E-step per row
+    block + the reference's numba ``_centers_dense``, k_means.py:572-582), row blocks = worker threads = host threads."""
     from oracle import kmeans_oracle as ok
     import subprocess
 
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle_c.so")):
         subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    # OpenBLAS in this image is built for at most 128 threads and aborts beyond that; 64 worker threads
-    # (one BLAS thread each) keep a safe margin on the many-core GPU hosts.  `cores` reports what was used.
-    cores = min(os.cpu_count() or 1, 64)
+    # every host thread; OpenBLAS in this image is built for at most 128 threads
+    cores = min(os.cpu_count() or 1, 128)
+    try:
+        cores = min(cores, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     X = synth_blobs_host(sample_rows, N_FEAT, N_CLUST, 0)
     init = X[:N_CLUST].copy()
-    blocks = ok.to_blocks(X, max(1, sample_rows // cores))
+    blocks = ok.to_blocks(X, max(1, -(-sample_rows // cores)))
     pool = ok.make_pool(cores)
-    limiter = None                                 # BLAS/OpenMP are pinned to 1 thread per task via the env above
+    mstep, mname = ok.centers_dense, "C scatter-add"
+    try:
+        ok.centers_dense_numba(X[:1000], np.zeros(1000, dtype=np.int32), N_CLUST)      # JIT warm-up
+        mstep, mname = ok.centers_dense_numba, "numba _centers_dense"
+    except Exception:
+        pass
     centers = init
     times = []
     for i in range(warm + iters):
         t0 = time.perf_counter()
-        _, _, centers = ok.lloyd_iteration(blocks, centers, N_CLUST, pool)
+        _, _, centers = ok.lloyd_iteration(blocks, centers, N_CLUST, pool, mstep=mstep)
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
     pool.shutdown()
     t = float(np.median(times))
     return {"value": sample_rows / t, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d of %d rows of the same workload, %d Lloyd iterations (median), %d row blocks on %d threads, "
-                      "scikit-learn float64 E-step + C scatter-add" % (sample_rows, N_ROWS, iters, len(blocks), cores),
-            "ms_per_iter": t * 1e3}
+            "sample": "%d of %d rows of C2, %d Lloyd iterations (median), %d row blocks on %d threads, "
+                      "scikit-learn float64 E-step + %s" % (sample_rows, N_ROWS, iters, len(blocks), cores, mname),
+            "ms_per_iter": t * 1e3, "host_threads": os.cpu_count(), "versions": _cpu_versions()}
+
+
+def c2_config(n):
+    return {"workload": "C2: synthetic blobs %d x %d float32 per GPU, k=%d, one chunk per GPU, fixed init (first k rows)"
+                        % (n, N_FEAT, N_CLUST),
+            "n_samples_per_gpu": n, "n_features": N_FEAT, "n_clusters": N_CLUST}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    sample = 1_000_000
-    res = cpu_lloyd_baseline(sample, max(1, args.steps), max(1, min(args.warmup, 2)))
+    n = args.rows
+    steps = max(1, args.steps)
+    res = cpu_lloyd_baseline(n, steps, max(1, min(args.warmup, 2)))
     line = {
-        "metric": METRIC, "value": res["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "metric": METRIC, "value": res["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": res["ms_per_iter"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C2 blobs 10M x 64 float32, k=256 (bounded sample of %d rows on host cores)" % sample,
-                   "n_features": N_FEAT, "n_clusters": N_CLUST},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": c2_config(n),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "host_threads", "versions")},
         "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# device-side helpers
+# ------------------------------------------------------------------------------------------
+def parity_check(X, labels, C_used, be, k, rows=1 << 20):
+    """Labels of the timed kernel on a slice of rows against the float64 arg-min evaluated on the device.
+    A mismatch is acceptable only where float64 itself is (nearly) tied: relative margin <= 1e-9."""
+    import torch
+
+    n = int(X.shape[0])
+    rows = min(rows, n)
+    # slice from the middle of the chunk (tile tails and CTA boundaries included)
+    s0 = max(0, (n - rows) // 2) // 32 * 32
+    C64 = C_used.double()
+    cn = (C64 * C64).sum(1)
+    mism = 0
+    worst = 0.0
+    for s in range(s0, s0 + rows, 1 << 17):
+        e = min(s + (1 << 17), s0 + rows)
+        xb = X[s:e].double()
+        d2 = (xb * xb).sum(1, keepdim=True) + cn[None, :] - 2.0 * xb @ C64.T
+        want = d2.argmin(1)
+        got = labels[s:e].long()
+        bad = got != want
+        nb = int(bad.sum())
+        if nb:
+            mism += nb
+            scale = (xb * xb).sum(1)[bad] + cn.max()
+            dg = d2[bad].gather(1, got[bad][:, None])[:, 0]
+            dw = d2[bad].gather(1, want[bad][:, None])[:, 0]
+            worst = max(worst, float(((dg - dw).abs() / scale).max()))
+    d = int(X.shape[1])
+    tdt = torch.float32 if X.dtype != torch.float64 else torch.float64
+    fam = int(be.kernel_family(d, k, X.dtype)) if hasattr(be, "kernel_family") else None
+    deferred = None
+    if fam == 1:
+        dr = be.deferred_rows(n, d, k, tdt)
+        deferred = None if dr is None else dr / float(n)
+    return {"rows": int(rows), "mismatches": int(mism), "worst_margin": worst,
+            "ok": bool(worst <= 1e-9), "deferred_frac": deferred}
+
+
+def time_lloyd(st, steps, warmup, barrier, world, dev):
+    """W untimed + K timed iterations of ``lloyd_loop`` (tol = 0: every iteration runs); returns (ms per step, mean ms
+    of the fused chunk kernel(s) inside a step, kernel launches of this library inside the timed region), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from dask_ml_b200.cluster.k_means import lloyd_loop
+
+    lloyd_loop(st, warmup, 0.0)
+    barrier()
+    kev = []
+    orig_step = st.step
+
+    def step_with_events():
+        pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        kev.append(pair)
+        orig_step(kernel_events=pair)
+
+    st.step = step_with_events
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = st.be.launch_count()
+    ev0.record()
+    lloyd_loop(st, steps, 0.0)
+    ev1.record()
+    barrier()
+    launches = st.be.launch_count() - l0
+    st.step = orig_step
+    ms_total = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]) / steps, float(t[1]), int(launches)
+
+
+def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
+    """One BASELINE shape as a sub-record: same loop, same parity check, HBM roofline."""
+    import torch
+    from dask_ml_b200.cluster.k_means import LloydState
+    from dask_ml_b200.engine import DeviceData
+
+    cfg = CONFIGS[name]
+    d, k = cfg["d"], cfg["k"]
+    if cfg["scaling"] == "strong":
+        n_total = cfg["n"]
+        per = -(-n_total // world)
+        lo, hi = rank * per, min(n_total, (rank + 1) * per)
+        # every rank generates the same stream and keeps its slice: the N-GPU job clusters the SAME rows
+        Xfull = synth_config_device(name, n_total, 0, dev)
+        X = Xfull[lo:hi].clone()
+        del Xfull
+        torch.cuda.empty_cache()
+    else:
+        n_total = cfg["n"] * world
+        X = synth_config_device(name, cfg["n"], rank, dev)
+    n_local = int(X.shape[0])
+    if d % 4 and be.kernel_family(d, k, X.dtype) == 1:
+        X = be.to_device(X, X.dtype)          # the tensor path wants a 16-byte row pitch (padded view)
+    data = DeviceData([X], be, comm)
+    init = data.global_rows(list(range(k))).astype(np.float64)
+    st = LloydState(data, init)
+    steps = max(5, args.steps)
+    ms, kern_ms, _ = time_lloyd(st, steps, args.warmup, barrier, world, dev)
+    C_used = st.C_new.clone()                 # after accept(): the centres the last E-step ran against
+    par = parity_check(X, st.labels[0], C_used, be, k)
+    esz = 2 if cfg["dtype"] == "bf16" else 4
+    bytes_alg = (d * esz + 4) * n_local
+    gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
+    flops = 2.0 * d * k * n_local
+    tf = flops / (kern_ms * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    t_hbm = bytes_alg / (float(peaks["hbm_gbs"]) * 1e9)
+    t_tc = flops / (peak_tf * 1e12)
+    bound = "hbm" if t_hbm >= t_tc else "tensor"
+    rec = {
+        "workload": cfg["what"], "scaling": cfg["scaling"], "n_total": int(n_total), "rows_per_gpu": n_local,
+        "n_features": d, "n_clusters": k, "dtype": cfg["dtype"], "row_pitch_elems": int(X.stride(0)),
+        "steps": steps, "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "samples/s",
+        "kernel_family": int(be.kernel_family(d, k, X.dtype)), "kernel_ms": kern_ms,
+        "roofline": {"bound": bound,
+                     "achieved": gbs if bound == "hbm" else tf, "peak": float(peaks["hbm_gbs"]) if bound == "hbm" else peak_tf,
+                     "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                     "frac": (gbs / float(peaks["hbm_gbs"])) if bound == "hbm" else tf / peak_tf,
+                     "hbm_gbs": gbs, "tflops": tf,
+                     "algorithmic": {"bytes_per_sample": d * esz + 4, "flops_per_sample": 2 * d * k}},
+        "parity_check": par, "final_shift": float(st.shift.item()),
+    }
+    del st, data, X
+    torch.cuda.empty_cache()
+    return rec
 
 
 # ------------------------------------------------------------------------------------------
@@ -184,9 +409,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU (default: the named workload)")
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU of the headline workload (default: C2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5s sub-records")
+    ap.add_argument("--configs", default="C3,C4,C5s", help="comma-separated sub-records to run")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 
@@ -209,12 +436,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from dask_ml_b200 import _lib
     from dask_ml_b200.cluster.k_means import LloydState, lloyd_iteration_host
     from dask_ml_b200.engine import Comm, CudaBackend, DeviceData
 
     be = CudaBackend(dev)
     comm = Comm()
+    peaks, peak_src = _peaks()
     n = args.rows
     X = synth_blobs_device(n, N_FEAT, N_CLUST, 1000 + rank, dev, torch.float32)
     data = DeviceData([X], be, comm)
@@ -228,37 +455,36 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ----
-    for _ in range(args.warmup):
-        st.step()
-        st.accept()
-    barrier()
-
-    # ---- timed region: K Lloyd iterations, device-resident X (2.56 GB per GPU >> 126 MB L2) ----
+    # ---- headline: W + K Lloyd iterations exactly as fit runs them (device-resident X, 2.56 GB per GPU >> L2) ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = be.launch_count()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        st.step(kernel_events=kev[i])
-        st.accept()
-    ev1.record()
-    barrier()
+    ms_per_step, kern_ms, launches = time_lloyd(st, args.steps, args.warmup, barrier, world, dev)
     clocks = sampler.stop()
-    launches = be.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, kern_ms = float(t[0]), float(t[1])
-    ms_per_step = ms_total / args.steps
     value = n * world / (ms_per_step * 1e-3)
     shift = float(st.shift.item())
+    C_used = st.C_new.clone()
+    par = parity_check(X, st.labels[0], C_used, be, N_CLUST)
+
+    # ---- latency of the per-iteration collective (N > 1) ----
+    allreduce_us = None
+    if world > 1:
+        buf = torch.zeros_like(st.red)
+        for _ in range(5):
+            comm.allreduce_sum_(buf)
+        barrier()
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        reps = 50
+        a0.record()
+        for _ in range(reps):
+            comm.allreduce_sum_(buf)
+        a1.record()
+        barrier()
+        ta = torch.tensor([a0.elapsed_time(a1) / reps * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_us = {"value": float(ta[0]), "payload_bytes": int(buf.numel() * 8),
+                        "how": "mean of %d back-to-back all-reduces of the step's [k*d+k+1] float64 buffer, CUDA events, max over ranks" % reps,
+                        "bus_gbs": float(buf.numel() * 8 * 2 * (world - 1) / world / (float(ta[0]) * 1e-6) / 1e9)}
 
     # ---- e2e: host-resident X, H2D inside the timed region, through the public host-buffer call ----
     e2e = None
@@ -292,13 +518,30 @@ def main():
                "d2h_bytes_per_step": int(N_CLUST * N_FEAT * 8 + 16), "ms_per_step": ems, "steps": e_steps,
                "api": "dask_ml_b200.cluster.k_means.lloyd_iteration_host (pinned host X, double-buffered H2D)"}
         del Xh
+    fam_c2 = int(be.kernel_family(N_FEAT, N_CLUST, torch.float32))
+    del st, data, X
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE shapes ----
+    configs = {}
+    if not args.no_configs:
+        for name in [c for c in args.configs.split(",") if c]:
+            if name not in CONFIGS or name == "C2":
+                continue
+            if CONFIGS[name]["dtype"] == "bf16" and not getattr(be, "supports_bf16", False):
+                configs[name] = {"workload": CONFIGS[name]["what"], "unavailable": "bf16 input is not supported by this build"}
+                continue
+            try:
+                configs[name] = run_config(name, args, be, comm, dev, rank, world, barrier, peaks)
+            except Exception as e:  # a sub-record must never take the headline down
+                configs[name] = {"workload": CONFIGS[name]["what"], "error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks, peak_src, tf32 = _peaks()
     flops = 2.0 * N_FEAT * N_CLUST * n
     bytes_alg = (N_FEAT * 4 + 4) * n
     ach_tf = flops / (kern_ms * 1e-3) / 1e12
@@ -316,7 +559,8 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {
         "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-        "traffic": traffic, "peak_source": peak_note, "kernel_ms": kern_ms,
+        "traffic": traffic, "traffic_source": "static: ncu --set full capture committed under profiles/ (not measured in this run)",
+        "peak_source": peak_note, "kernel_ms": kern_ms,
         "kernel": "tc_chunk_kernel<true,false> (tcgen05 split-fp16 fused E+M) + tc_recheck + reduce_partials",
         "issued": {"tflops": ach_tf * issued_ratio, "frac": ach_tf * issued_ratio / peak_tf,
                    "note": "tensor-pipe work actually issued: 3 fp16 products + ||c||^2 step per algorithmic product"},
@@ -327,20 +571,20 @@ def main():
     }
     cpu = None
     if not args.no_cpu:
-        cpu = cpu_lloyd_baseline(500_000, 3, 1)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_lloyd_baseline(1_000_000, 3, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "host_threads", "versions")}
+    cfg = c2_config(n)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: synthetic blobs %d x %d float32 per GPU, k=%d, one chunk per GPU, fixed init (first k rows)"
-                               % (n, N_FEAT, N_CLUST),
-                   "n_samples_per_gpu": n, "n_features": N_FEAT, "n_clusters": N_CLUST,
-                   "arithmetic": "split-fp16 (hi,lo) x3 product on tcgen05 kind::f16, fp32 accumulate, float64 re-check of near-ties + float64 centre update",
+        "config": cfg,
+        "detail": {"arithmetic": "split-fp16 (hi,lo) x3 product on tcgen05 kind::f16, fp32 accumulate, float64 re-check of near-ties + float64 centre update",
                    "l2": "inputs (%.2f GB per GPU) are larger than L2 (126 MB); no explicit flush" % (n * N_FEAT * 4 / 1e9),
-                   "kernel_family": int(be.kernel_family(N_FEAT, N_CLUST, torch.float32)),
-                   "final_shift": shift},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                   "step": "lloyd_loop(): pack + fused E+M kernel + re-check + reduce (+ all-reduce) + finalize + ONE host read of the shift per iteration, as KMeans.fit runs it",
+                   "kernel_family": fam_c2, "final_shift": shift},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": par,
+        "allreduce_us": allreduce_us, "configs": configs, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -45,6 +45,8 @@ SIGNATURES = {
     "bkm_debug_abort_code": (ctypes.c_uint, []),
     "bkm_debug_abort_detail": (None, [_c_void_p]),
     "bkm_debug_trace": (_int, [_c_void_p, _int]),
+    "bkm_debug_reset": (None, []),
+    "bkm_debug_deferred_rows": (_int, [_c_void_p, _i64, _int, _int, _int, ctypes.POINTER(_int)]),
 }
 
 _lib = None

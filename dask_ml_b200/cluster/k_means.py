@@ -336,6 +336,13 @@ class _AssignPass(object):
         X.comm.allreduce_sum_(acc)
         return labels, mins, acc
 
+    def cost(self, centers64):
+        """phi = sum of min squared distances, as a checked host float."""
+        _, _, acc = self.run(centers64, squared=True)
+        v = float(acc.item())
+        _check_engine(self.be, v, "the k-means|| cost")
+        return v
+
 
 @_timed(_logger=logger)
 def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_factor=2):
@@ -492,6 +499,41 @@ class LloydState(object):
         return acc
 
 
+def _check_engine(be, value, what):
+    """A tcgen05 pipeline wait that timed out poisons the step with NaN (bkm_tc.cu): turn that into an error."""
+    if value == value and abs(value) != float("inf"):
+        return
+    code = be.abort_code() if hasattr(be, "abort_code") else 0
+    if code:
+        be.reset_abort()
+        raise RuntimeError("B200 KMeans engine: a pipeline wait inside the tensor kernel timed out (abort code 0x%08x) "
+                           "while computing %s; the results of this call are invalid" % (code, what))
+    raise RuntimeError("B200 KMeans engine: non-finite %s (%r) — X or the centres hold values outside the range of "
+                       "their dtype" % (what, value))
+
+
+def lloyd_loop(st, max_iter, tol):
+    """The Lloyd iterations of k_means.py:522-560 over a ``LloydState``: one ``step()`` (fused E+M kernels, all-reduce,
+    centre update) and ONE host synchronisation (the shift, k_means.py:552) per iteration.  ``bench.py`` times this very
+    function.  Returns ``(shift, index of the last iteration, accepted)``; ``accepted`` tells whether ``st.C`` already
+    holds the centres computed by the last iteration (False after the convergence ``break``, Q3)."""
+    shift = None
+    i = -1
+    accepted = False
+    for i in range(max_iter):
+        with _timer("Lloyd loop %2d." % i, _logger=logger):
+            st.step()
+            shift = float(st.shift.item())       # the one host sync per iteration (k_means.py:552)
+            _check_engine(st.be, shift, "the centre shift")
+            logger.info("Shift: %0.4f", shift)
+            accepted = False
+            if shift < tol:
+                break                            # Q3: break BEFORE centers = new_centers
+            st.accept()
+            accepted = True
+    return shift, i, accepted
+
+
 def _kmeans_single_lloyd(
     X,
     n_clusters,
@@ -517,19 +559,7 @@ def _kmeans_single_lloyd(
     )
     dt = X.np_dtype
     st = LloydState(X, np.asarray(centers))
-    shift = None
-    i = -1
-    accepted = False
-    for i in range(max_iter):
-        with _timer("Lloyd loop %2d." % i, _logger=logger):
-            st.step()
-            shift = float(st.shift.item())       # the one host sync per iteration (k_means.py:552)
-            logger.info("Shift: %0.4f", shift)
-            accepted = False
-            if shift < tol:
-                break                            # Q3: break BEFORE centers = new_centers
-            st.accept()
-            accepted = True
+    shift, i, accepted = lloyd_loop(st, max_iter, tol)
 
     if shift is None:
         raise ValueError("max_iter must be at least 1, got %r" % (max_iter,))
@@ -537,6 +567,7 @@ def _kmeans_single_lloyd(
     if shift > 1e-7:
         # Q4: re-label against the current centres with the default (non-squared) metric
         inertia = float(st.relabel(squared=False).item())
+        _check_engine(st.be, inertia, "the inertia")
     else:
         # Q4, other side: inertia = sum of the SQUARED distances of the last E-step, i.e. against the
         # centres that E-step used.  The loop does not keep per-row distances, so they are produced here
@@ -544,6 +575,7 @@ def _kmeans_single_lloyd(
         if accepted:
             st.accept()                          # back to the centres of the last E-step
         inertia = float(st.relabel(squared=True).item())
+        _check_engine(st.be, inertia, "the inertia")
         if accepted:
             st.accept()
 

@@ -6,6 +6,7 @@
 namespace bkm {
 unsigned int tc_abort_code();
 void tc_abort_detail(unsigned int* out64);
+void tc_abort_reset();
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s);
 int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
                     double* shift, int k, int d, cudaStream_t s);
@@ -16,17 +17,17 @@ int launch_transform(const void* X, long long n, int d, long long ldx, int dtype
 int launch_check_finite(const void* X, long long n, int d, long long ldx, int dtype, int* flag,
                         int sm_count, cudaStream_t s);
 
-static int g_sm_count[64];
+static std::atomic<int> g_sm_count[64];
 static int sm_count_of_current(int* out) {
   int dev = 0;
   BKM_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return BKM_EINVAL;
-  if (g_sm_count[dev] == 0) {
-    int v = 0;
+  int v = g_sm_count[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
     BKM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-    g_sm_count[dev] = v;
+    g_sm_count[dev].store(v, std::memory_order_relaxed);
   }
-  *out = g_sm_count[dev];
+  *out = v;
   return 0;
 }
 
@@ -45,6 +46,7 @@ static float tau_for(int d, int dtype, int flags, int family) {
   // worst margin of a label that differs from float64 = 4.8e-7; the bound below (3.3e-6 at d=64) leaves ~7x
   // headroom, and the parity tests assert that every remaining difference is a float64 near-tie (<= 1e-9).
   if (family == 1) return (8.0f * sqrtf(3.0f * (float)((d + 7) / 8)) + 16.0f) * eps;
+  // CUDA-core kernels (generic and streaming): fp32 FMA chains of length d plus the rounding of ||c||^2
   return 8.0f * (sqrtf((float)d) + 2.0f) * eps;
 }
 
@@ -58,12 +60,12 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (mstep && (!sums || !counts)) return BKM_EINVAL;
   if (n == 0) return 0;
   if (!X) return BKM_EINVAL;
-  WsLayout W = ws_layout(n, d, k, x_dtype);
-  if (ws_bytes < W.total) return BKM_EWORKSPACE;
-  if (n > 0x7fffffffLL) return BKM_EUNSUPPORTED;      // row indices inside a chunk are 32-bit
   int sm = 0;
   int rc = sm_count_of_current(&sm);
   if (rc) return rc;
+  WsLayout W = ws_layout(n, d, k, x_dtype, sm);
+  if (ws_bytes < W.total) return BKM_EWORKSPACE;
+  if (n > 0x7fffffffLL) return BKM_EUNSUPPORTED;      // row indices inside a chunk are 32-bit
 
   ChunkArgs a;
   a.X = X; a.n = n; a.d = d; a.ldx = ldx;
@@ -74,6 +76,8 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   a.pcnt = (int*)((unsigned char*)ws + W.off_pcnt);
   a.pin = (double*)((unsigned char*)ws + W.off_pin);
   a.want_sum = dist_sum != nullptr;
+  a.psum_slots = W.psum_slots;
+  a.part_slots = W.part_slots;
   a.defer_cnt = (int*)((unsigned char*)ws + W.off_flag);
   a.defer_idx = (int*)((unsigned char*)ws + W.off_defer);
   a.out_sums = sums; a.out_counts = counts; a.out_dist_sum = dist_sum;
@@ -86,6 +90,13 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (family == 1) {
     rc = launch_tc(a, mstep, sm, &grid, s);
     if (rc == BKM_EALIGN && !(flags & BKM_FLAG_FORCE_TC)) {   // TMA needs 16-byte aligned rows
+      family = 0;
+      a.tau = tau_for(d, x_dtype, flags, 0);
+    }
+  }
+  if (family == 2) {
+    rc = launch_stream(a, mstep, sm, &grid, s);
+    if (rc == BKM_EALIGN || rc == BKM_EUNSUPPORTED) {          // odd base pointer / very wide pitch: generic kernel
       family = 0;
       a.tau = tau_for(d, x_dtype, flags, 0);
     }
@@ -134,8 +145,9 @@ int bkm_kernel_family(int d, int k, int x_dtype, int flags) {
   bool tc = tc_supported(d, k, x_dtype);
   if (flags & BKM_FLAG_FORCE_SIMT) return 0;
   if (flags & BKM_FLAG_FORCE_TC) return tc ? 1 : BKM_EUNSUPPORTED;
-  // The tensor kernel costs ~20 ns per row and SM whatever k and d are (per-tile pipeline costs), the
-  // CUDA-core kernel ~11 + 0.017 k d (measured, r01): tiny problems (C4: d=13, k=20) stay on the CUDA cores.
+  // The tensor kernel costs ~20 ns per row and SM whatever k and d are (per-tile pipeline costs): tiny problems
+  // (C4: d=13, k=20) are HBM-bound and go to the streaming CUDA-core kernel (family 2, bkm_stream.cu).
+  if (stream_supported(d, k, x_dtype) && (long long)k * d < 512) return 2;
   return (tc && (long long)k * d >= 512) ? 1 : 0;
 }
 
@@ -158,7 +170,9 @@ int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype, void* p
 int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out) {
   if (k <= 0 || d <= 0 || n < 0 || !out) return BKM_EINVAL;
   if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
-  *out = ws_layout(n, d, k, x_dtype).total;
+  int sm = 0;
+  if (sm_count_of_current(&sm)) sm = kDefaultSMs;       // no device (CPU-side sizing): the B200 figure
+  *out = ws_layout(n, d, k, x_dtype, sm).total;
   return 0;
 }
 
@@ -220,10 +234,21 @@ int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, 
   return launch_check_finite(X, n, d, ldx, x_dtype, flag, sm, (cudaStream_t)stream);
 }
 
-int64_t bkm_launch_count(void) { return (int64_t)g_launches; }
+int64_t bkm_launch_count(void) { return (int64_t)g_launches.load(); }
 
 unsigned int bkm_debug_abort_code(void) { return bkm::tc_abort_code(); }
 void bkm_debug_abort_detail(unsigned int* out64_host) { bkm::tc_abort_detail(out64_host); }
+void bkm_debug_reset(void) { bkm::tc_abort_reset(); }
+
+int bkm_debug_deferred_rows(const void* workspace, int64_t n, int d, int k, int x_dtype, int* count_host) {
+  if (!workspace || !count_host || n < 0 || d <= 0 || k <= 0) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  int sm = 0;
+  if (sm_count_of_current(&sm)) sm = kDefaultSMs;
+  WsLayout W = ws_layout(n, d, k, x_dtype, sm);
+  BKM_CUDA_TRY(cudaMemcpy(count_host, (const unsigned char*)workspace + W.off_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
 int bkm_debug_trace(long long* out_host, int n) { return bkm::tc_trace(out_host, n); }
 
 }  // extern "C"

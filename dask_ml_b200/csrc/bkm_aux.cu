@@ -3,10 +3,11 @@
 #include "bkm_common.cuh"
 #include <math_constants.h>
 #include <cuda_fp16.h>
+#include <atomic>
 
 namespace bkm {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 // ---------------------------------------------------------------------------------------
 // pack_centers: float64 centres [k][d] -> every layout the kernels read (see PackLayout).
@@ -332,16 +333,19 @@ int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
 
 // ---------------------------------------------------------------------------------------
 // finalize: C' = sums / max(counts,1) ; shift = ||C - C'||_F^2   (k_means.py:548-555)
-// up to 64 CTAs; the last one to finish adds the per-CTA parts in CTA order -> deterministic shift
-// (one finalize at a time per device: the scratch is a device global).
+// up to 64 CTAs; the last one to finish adds the per-CTA parts in CTA order -> deterministic shift.
+// The per-launch scratch is one of 32 slots handed out round-robin by the host (an atomic counter), so finalize calls
+// of different estimators / streams / host threads in flight at the same time never share one.
 // ---------------------------------------------------------------------------------------
-__device__ double g_fin_part[64];
-__device__ unsigned int g_fin_done = 0;
+static const int kFinSlots = 32;
+__device__ double g_fin_part[kFinSlots][64];
+__device__ unsigned int g_fin_done[kFinSlots];
+static std::atomic<unsigned int> g_fin_seq{0};
 
 __global__ void __launch_bounds__(1024)
 finalize_kernel(const double* __restrict__ sums, const long long* __restrict__ counts,
                 const double* __restrict__ Cold, double* __restrict__ Cnew,
-                double* shift, int k, int d) {
+                double* shift, int k, int d, int slot) {
   __shared__ double sm[32];
   __shared__ bool last;
   double acc = 0.0;
@@ -360,25 +364,26 @@ finalize_kernel(const double* __restrict__ sums, const long long* __restrict__ c
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
-    g_fin_part[blockIdx.x] = s;
+    g_fin_part[slot][blockIdx.x] = s;
     __threadfence();
-    last = atomicAdd(&g_fin_done, 1u) == gridDim.x - 1;
+    last = atomicAdd(&g_fin_done[slot], 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
     // the last CTA to finish adds the per-CTA parts in CTA order: deterministic shift
     __threadfence();
     double s = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += *(volatile double*)&g_fin_part[b];
+    for (int b = 0; b < (int)gridDim.x; ++b) s += *(volatile double*)&g_fin_part[slot][b];
     *shift = s;
-    g_fin_done = 0;
+    g_fin_done[slot] = 0;
   }
 }
 
 int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
                     double* shift, int k, int d, cudaStream_t s) {
   int nb = (k * d + 1023) / 1024; if (nb > 64) nb = 64; if (nb < 1) nb = 1;
-  finalize_kernel<<<nb, 1024, 0, s>>>(sums, counts, Cold, Cnew, shift, k, d);
+  const int slot = (int)(g_fin_seq.fetch_add(1u) % kFinSlots);
+  finalize_kernel<<<nb, 1024, 0, s>>>(sums, counts, Cold, Cnew, shift, k, d, slot);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "../../include/bkm_b200.h"
 
 #define BKM_CUDA_TRY(expr)                                  \
@@ -14,8 +15,8 @@
 namespace bkm {
 
 // Counts kernel launches enqueued by the library (bench.py reports it as gpu_launches).
-extern long long g_launches;
-inline void note_launch(int n = 1) { g_launches += n; }
+extern std::atomic<long long> g_launches;
+inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -68,19 +69,34 @@ struct PackHeader {
 // ---------------------------------------------------------------------------------------
 // Workspace for one chunk call: per-CTA partials.  Sized for the largest grid we launch.
 // ---------------------------------------------------------------------------------------
-static const int kMaxGrid = 148 * 8;
+// Per-CTA partial sums: one [k*d] slot per CTA of the largest grid a CUDA-core kernel launches (8 CTAs per SM),
+// fewer when a slot is large (a kernel whose per-CTA sums occupy most of the shared memory runs 1-2 CTAs per SM), and a
+// single slot when k*d cannot be CTA-resident at all (generic kernel's GLOBAL mode: atomics into slot 0).
+static const int kDefaultSMs = 148;
 
 struct WsLayout {
   size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, total;
   size_t psum_esz;
+  int psum_slots;     // capacity of off_psum in [k*d] slots
+  int part_slots;     // capacity of off_pcnt / off_pin (per-CTA counts / distance sums): the largest grid
 };
-static inline WsLayout ws_layout(long long n, int d, int k, int dtype) {
+static inline WsLayout ws_layout(long long n, int d, int k, int dtype, int sm_count = kDefaultSMs) {
   WsLayout W;
+  if (sm_count <= 0) sm_count = kDefaultSMs;
   W.psum_esz = dtype == BKM_F64 ? 8 : 4;
+  const size_t slot = (size_t)k * d * W.psum_esz;
+  W.part_slots = sm_count * 8;
+  if (2 * slot > 227 * 1024) W.psum_slots = 1;                 // cannot be CTA-resident: global accumulation
+  else {
+    size_t per_sm = (227 * 1024) / (2 * slot);                  // CTAs per SM that could hold centres + sums
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    W.psum_slots = (int)(sm_count * per_sm);
+  }
   size_t o = 0;
-  W.off_psum = o; o = align_up(o + (size_t)kMaxGrid * k * d * W.psum_esz, 256);
-  W.off_pcnt = o; o = align_up(o + (size_t)kMaxGrid * k * 4, 256);
-  W.off_pin = o;  o = align_up(o + (size_t)kMaxGrid * 8, 256);
+  W.off_psum = o; o = align_up(o + (size_t)W.psum_slots * slot, 256);
+  W.off_pcnt = o; o = align_up(o + (size_t)W.part_slots * k * 4, 256);
+  W.off_pin = o;  o = align_up(o + (size_t)W.part_slots * 8, 256);
   W.off_flag = o; o = align_up(o + 256, 256);          // [0] = deferred-row counter
   W.off_defer = o; o = align_up(o + (size_t)(n > 0 ? n : 0) * 4, 256);
   W.total = o;
@@ -106,6 +122,8 @@ struct ChunkArgs {
   int want_sum;       // caller wants the summed min distance (inertia / cost)
   int* defer_cnt;     // tcgen05 path: number of rows deferred to the float64 re-check kernel
   int* defer_idx;     // [n] their row indices
+  int psum_slots;     // capacity of psum in [k*d] slots (grid clamp of the kernels that keep per-CTA sums)
+  int part_slots;     // capacity of pcnt / pin
   double* out_sums;   // final accumulators (the re-check kernel adds the deferred rows' contributions)
   long long* out_counts;
   double* out_dist_sum;
@@ -117,6 +135,9 @@ int launch_simt(const ChunkArgs& a, bool mstep, int dtype, int sm_count, int* gr
 bool tc_supported(int d, int k, int dtype);
 int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
 int tc_trace(long long* out, int n);
+// implemented in bkm_stream.cu
+bool stream_supported(int d, int k, int dtype);
+int launch_stream(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
 // implemented in bkm_aux.cu
 int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
                            double* sums, long long* counts, double* dist_sum, cudaStream_t s);

@@ -50,9 +50,12 @@ template <typename T> __host__ __device__ inline int tile_pitch(int d4) {
 
 struct SimtSmem {
   size_t off_cs, off_cns, off_xs, off_lab, off_red2, off_flist, off_sums, off_cnts, off_misc, total;
+  int rt;     // rows per tile (<= TILE; smaller for very wide rows so that the staged tile still fits shared memory)
 };
+static const size_t kSmemBudget = 227 * 1024;
+
 template <typename T>
-static inline SimtSmem simt_smem(int k, int d, int J, bool mstep, bool global_mode) {
+static inline SimtSmem simt_smem(int k, int d, int J, bool mstep, bool global_mode, int rt = TILE) {
   typedef typename PsumT<T>::type PS;
   int d4 = (d + 3) / 4 * 4;
   int kJ = (k + J - 1) / J * J;
@@ -61,7 +64,8 @@ static inline SimtSmem simt_smem(int k, int d, int J, bool mstep, bool global_mo
   S.off_cs = o;   if (!global_mode) o += (size_t)kJ * d4 * sizeof(T);
   o = align_up(o, 16);
   S.off_cns = o;  o += (size_t)kJ * sizeof(T); o = align_up(o, 16);
-  S.off_xs = o;   o += (size_t)TILE * pitch * sizeof(T); o = align_up(o, 16);
+  S.rt = rt;
+  S.off_xs = o;   o += (size_t)rt * pitch * sizeof(T); o = align_up(o, 16);
   S.off_lab = o;  o += TILE * 4;
   S.off_red2 = o; o += TILE * 8;
   S.off_flist = o; o += TILE * 4;
@@ -72,6 +76,13 @@ static inline SimtSmem simt_smem(int k, int d, int J, bool mstep, bool global_mo
   S.off_misc = o; o += 256;
   S.total = o;
   return S;
+}
+
+// Centres + per-CTA sums resident in shared memory (SMEM mode) need room for at least a 32-row tile next to them;
+// otherwise centres are read through L1/L2 and the sums go to global atomics (GLOBAL mode).
+template <typename T>
+static inline bool simt_mode_global(int k, int d, int J, bool mstep) {
+  return simt_smem<T>(k, d, J, mstep, false, 32).total > kSmemBudget;
 }
 
 template <typename T, int J, bool MSTEP, bool GLOBAL, bool SMALLK>
@@ -110,7 +121,8 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
     if (!GLOBAL) for (int i = tid; i < k * d; i += TILE) sums_s[i] = PS(0);
     for (int i = tid; i < k; i += TILE) cnts_s[i] = 0;
   }
-  for (int i = tid; i < TILE * pitch; i += TILE) xs[i] = T(0);
+  const int RT = S.rt;
+  for (int i = tid; i < RT * pitch; i += TILE) xs[i] = T(0);
   const T cnmax = (T)hdr->cn_max;
   double inertia_acc = 0.0;
   // Few clusters (k <= 32, d <= 16; BASELINE C4 / C1): lane j of every warp owns cluster j and keeps the sums of the
@@ -124,7 +136,7 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   int lcnt = 0;
   __syncthreads();
 
-  const long long ntiles = (a.n + TILE - 1) / TILE;
+  const long long ntiles = (a.n + RT - 1) / RT;
   // rows with a small padding (the 16-byte pitch the tensor path wants, e.g. 13 -> 16) are streamed like
   // contiguous ones: the whole [rows][ldx] block is read with 16-byte loads and the padding is dropped
   const int L = (int)a.ldx;
@@ -132,14 +144,14 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
                        (a.ldx == d || (a.ldx <= d + 8 && (a.ldx * sizeof(T)) % 16 == 0));
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long r0 = tile * TILE;
-    const int rows = (int)min((long long)TILE, a.n - r0);
+    const long long r0 = tile * RT;
+    const int rows = (int)min((long long)RT, a.n - r0);
 
     // ---- stage the tile: coalesced loads, [row][pitch] layout in smem ----
-    if (flat_ok) {
+    if (flat_ok && ((r0 * (long long)L * (long long)sizeof(T)) & 15) == 0) {
       const int per16 = 16 / (int)sizeof(T);
       const long long nelem = (long long)rows * L;
-      const T* src = X + r0 * (long long)L;     // 16-byte aligned: r0 is a multiple of TILE
+      const T* src = X + r0 * (long long)L;     // 16-byte aligned (checked above)
       const long long nvec = nelem / per16;
       for (long long v = tid; v < nvec; v += TILE) {
         T e[4];
@@ -354,17 +366,28 @@ simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
   }
 }
 
+// Rows per tile: TILE unless the staged rows would not fit next to the other buffers (very wide rows: d in the hundreds
+// or thousands run with fewer rows per tile; the idle threads of the thread-per-row E-step are the price).
+template <typename T>
+static int pick_rt(int k, int d, int J, bool mstep, bool global_mode) {
+  int rt = TILE;
+  while (rt > 1 && simt_smem<T>(k, d, J, mstep, global_mode, rt).total > kSmemBudget) rt = rt > 32 ? rt - 32 : rt / 2;
+  return rt;
+}
+
 template <typename T, int J, bool MSTEP, bool GLOBAL, bool SMALLK = false>
 static int launch_one(const ChunkArgs& a, int sm_count, int* grid_out, cudaStream_t s) {
-  SimtSmem S = simt_smem<T>(a.k, a.d, J, MSTEP, GLOBAL);
+  SimtSmem S = simt_smem<T>(a.k, a.d, J, MSTEP, GLOBAL, pick_rt<T>(a.k, a.d, J, MSTEP, GLOBAL));
+  if (S.total > kSmemBudget) return BKM_EUNSUPPORTED;
   auto kern = simt_chunk_kernel<T, J, MSTEP, GLOBAL, SMALLK>;
   BKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
   int occ = 0;
   BKM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, S.total));
   if (occ < 1) return BKM_EUNSUPPORTED;
-  long long ntiles = (a.n + TILE - 1) / TILE;
+  long long ntiles = (a.n + S.rt - 1) / S.rt;
   long long grid = (long long)sm_count * occ;
-  if (grid > kMaxGrid) grid = kMaxGrid;
+  if (MSTEP && !GLOBAL && grid > a.psum_slots) grid = a.psum_slots;
+  if (grid > a.part_slots) grid = a.part_slots;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   *grid_out = (int)grid;
@@ -374,16 +397,13 @@ static int launch_one(const ChunkArgs& a, int sm_count, int* grid_out, cudaStrea
   return 0;
 }
 
-static const size_t kSmemBudget = 227 * 1024;
-
 template <typename T>
 static int launch_T(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
   const int k = a.k;
   int waste8 = (k + 7) / 8 * 8 - k, waste16 = (k + 15) / 16 * 16 - k;
   bool use16 = waste16 <= waste8 && sizeof(T) == 4;
   int J = use16 ? 16 : 8;
-  bool global_mode = simt_smem<T>(k, a.d, J, mstep, false).total > kSmemBudget;
-  if (global_mode && simt_smem<T>(k, a.d, J, mstep, true).total > kSmemBudget) return BKM_EUNSUPPORTED;
+  bool global_mode = simt_mode_global<T>(k, a.d, J, mstep);
 #define BKM_DISPATCH(JJ)                                                                   \
   if (mstep) {                                                                             \
     if (global_mode) return launch_one<T, JJ, true, true>(a, sm_count, grid_out, s);       \
@@ -404,14 +424,14 @@ int launch_simt(const ChunkArgs& a, bool mstep, int dtype, int sm_count, int* gr
   bool global_mode;
   if (dtype == BKM_F32) {
     int J = ((a.k + 15) / 16 * 16 - a.k) <= ((a.k + 7) / 8 * 8 - a.k) ? 16 : 8;
-    global_mode = simt_smem<float>(a.k, a.d, J, mstep, false).total > kSmemBudget;
+    global_mode = simt_mode_global<float>(a.k, a.d, J, mstep);
     if (global_mode && mstep) {
       BKM_CUDA_TRY(cudaMemsetAsync(a.psum, 0, (size_t)a.k * a.d * sizeof(float), s));
       note_launch();
     }
     rc = launch_T<float>(a, mstep, sm_count, grid_out, s);
   } else {
-    global_mode = simt_smem<double>(a.k, a.d, 8, mstep, false).total > kSmemBudget;
+    global_mode = simt_mode_global<double>(a.k, a.d, 8, mstep);
     if (global_mode && mstep) {
       BKM_CUDA_TRY(cudaMemsetAsync(a.psum, 0, (size_t)a.k * a.d * sizeof(double), s));
       note_launch();

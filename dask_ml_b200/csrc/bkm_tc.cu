@@ -126,18 +126,30 @@ __device__ long long g_tc_trace[16 * 128];
 #define TRACE(slot, it) do { } while (0)
 #endif
 __device__ unsigned int g_tc_dbg[64];     // per-warp abort code of the first CTA that aborts (debug)
+__device__ __forceinline__ unsigned long long tc_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait limits are WALL-CLOCK (2 s): spin counts shrink under ncu replay, compute-sanitizer or time-slicing.
+static const unsigned long long TC_WAIT_LIMIT_NS = 2000000000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // suspend-time hint: the hardware
         "selp.u32 %0, 1, 0, p;\n}"                                        // parks the warp instead of polling
         : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
-    if (spin > (1u << 18) || ((spin & 15) == 15 && *(volatile unsigned int*)&g_tc_abort)) {
-      atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
-      if (spin > 2048 && (threadIdx.x & 31) == 0) g_tc_dbg[threadIdx.x >> 5] = 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | blockIdx.x;
-      return;
+    if (!done && (spin & 15) == 15) {
+      const unsigned long long now = tc_now_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > TC_WAIT_LIMIT_NS || *(volatile unsigned int*)&g_tc_abort) {
+        atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
+        if ((threadIdx.x & 31) == 0) g_tc_dbg[threadIdx.x >> 5] = 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | blockIdx.x;
+        return;
+      }
     }
   }
 }
@@ -154,6 +166,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 // issue slots from the warps doing the work on the same SM sub-partition.
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -161,9 +174,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (!done) __nanosleep(256);
-    if (spin > (1u << 20) || ((spin & 15) == 15 && *(volatile unsigned int*)&g_tc_abort)) {
-      atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
-      return;
+    if (!done && (spin & 15) == 15) {
+      const unsigned long long now = tc_now_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > TC_WAIT_LIMIT_NS || *(volatile unsigned int*)&g_tc_abort) {
+        atomicCAS(&g_tc_abort, 0u, 0x80000000u | ((bar & 0xfff) << 12) | (parity << 8) | (threadIdx.x >> 5));
+        return;
+      }
     }
   }
 }
@@ -366,6 +383,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       const long long m_total = cfg.mring ? qpt * my_tiles : 0;
       long long ait = 0, mi = 0;
       uint32_t idle = 0;
+      unsigned long long idle_t0 = 0;
 #pragma unroll 1
       while (ait < my_tiles || mi < m_total) {
         bool progressed = false;
@@ -396,11 +414,15 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
             progressed = true;
           }
         }
-        if (progressed) { idle = 0; continue; }
+        if (progressed) { idle = 0; idle_t0 = 0; continue; }
         __nanosleep(64);
-        if (++idle > (1u << 22) || ((idle & 255) == 255 && *(volatile unsigned int*)&g_tc_abort)) {
-          atomicCAS(&g_tc_abort, 0u, 0x80000000u | (0xfffu << 12));
-          break;
+        if ((++idle & 255) == 255) {
+          const unsigned long long now = tc_now_ns();
+          if (idle_t0 == 0) idle_t0 = now;
+          if (now - idle_t0 > TC_WAIT_LIMIT_NS || *(volatile unsigned int*)&g_tc_abort) {
+            atomicCAS(&g_tc_abort, 0u, 0x80000000u | (0xfffu << 12));
+            break;
+          }
         }
       }
     }
@@ -1037,6 +1059,13 @@ int tc_trace(long long* out, int n) {
 #endif
 }
 void tc_abort_detail(unsigned int* out64) { cudaMemcpyFromSymbol(out64, g_tc_dbg, 64 * sizeof(unsigned int)); }
+// Clear the sticky abort word (after the host has reported it): later launches run normally again.
+void tc_abort_reset() {
+  const unsigned int z = 0;
+  unsigned int zz[64] = {0};
+  cudaMemcpyToSymbol(g_tc_abort, &z, sizeof(z));
+  cudaMemcpyToSymbol(g_tc_dbg, zz, sizeof(zz));
+}
 
 bool tc_supported(int d, int k, int dtype) {
   // any d <= 64: columns beyond d are zero-filled by TMA; what TMA does need is a 16-byte row pitch and base

@@ -110,6 +110,23 @@ class CudaBackend(object):
     def launch_count(self):
         return int(self.lib.bkm_launch_count())
 
+    def abort_code(self):
+        """Non-zero once a pipeline wait of the tensor kernel has timed out (synchronises the device)."""
+        return int(self.lib.bkm_debug_abort_code())
+
+    def reset_abort(self):
+        self.lib.bkm_debug_reset()
+
+    def deferred_rows(self, n, d, k, dtype):
+        """Rows the last tensor-path chunk call of this shape handed to the float64 re-check (debug / bench)."""
+        ws = self._ws.get("buf")
+        if ws is None:
+            return None
+        c = ctypes.c_int(0)
+        _lib.check(self.lib.bkm_debug_deferred_rows(self._ptr(ws), int(n), d, k, _DT_CODE[dtype], ctypes.byref(c)),
+                   "bkm_debug_deferred_rows")
+        return int(c.value)
+
     # -- data ----------------------------------------------------------------------------
     def to_device(self, block, dtype):
         """numpy / torch block -> contiguous CUDA tensor of `dtype` (torch dtype)."""

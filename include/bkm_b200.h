@@ -66,7 +66,9 @@ const char* bkm_error_string(int code);
 int bkm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
 /* Which kernel family a (d, k, dtype, flags) problem dispatches to:
- * 0 = SIMT (CUDA cores, fp32/fp64 exact), 1 = tcgen05 tensor-core path (split-fp16 x3 product, fp32 accumulate). <0 = error. */
+ * 0 = generic CUDA-core kernel (any d/k, fp32/fp64), 1 = tcgen05 tensor-core path (split-fp16 x3 product, fp32
+ * accumulate; d <= 64, k <= 256), 2 = streaming CUDA-core kernel for tiny k*d (HBM-bound shapes: d <= 16, k <= 32).
+ * <0 = error. */
 int bkm_kernel_family(int d, int k, int x_dtype, int flags);
 
 /* ---- centre pack -------------------------------------------------------------------
@@ -140,6 +142,12 @@ int64_t bkm_launch_count(void);
  * instead of hanging); encodes barrier / parity / warp.  Synchronises the device. */
 unsigned int bkm_debug_abort_code(void);
 void bkm_debug_abort_detail(unsigned int* out64_host);   /* per-warp wait that timed out (64 words) */
+/* Clears the abort word once the host has reported it (the host side raises RuntimeError on a non-finite shift /
+ * cost and calls this, so that one timed-out wait does not poison the process).  Synchronises the device. */
+void bkm_debug_reset(void);
+/* Number of rows the LAST tcgen05 chunk call that used `workspace` (same n, d, k, dtype) deferred to the float64
+ * re-check (near-ties and out-of-range rows).  Synchronises the device; used by bench.py's parity record. */
+int bkm_debug_deferred_rows(const void* workspace, int64_t n, int d, int k, int x_dtype, int* count_host);
 /* `make TRACE=1` builds only: SM-clock timeline of CTA 0 (16 events x 128 tiles); returns words written, 0 otherwise */
 int bkm_debug_trace(long long* out_host, int n);
 

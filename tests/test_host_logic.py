@@ -42,7 +42,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.bkm_kernel_family(64, 256, 0, 0) == 1      # tcgen05 path
     assert lib.bkm_kernel_family(41, 100, 0, 0) == 1      # tcgen05 too (given a 16-byte row pitch; else the launch falls back)
     assert lib.bkm_kernel_family(100, 100, 0, 0) == 0     # CUDA-core path: d > 64
-    assert lib.bkm_kernel_family(13, 20, 0, 0) == 0       # CUDA-core path: tiny k*d (per-tile costs of the tensor pipeline)
+    assert lib.bkm_kernel_family(13, 20, 0, 0) == 2       # streaming CUDA-core kernel: tiny k*d is HBM-bound
+    assert lib.bkm_kernel_family(13, 20, 0, 1) == 0       # FORCE_SIMT -> the generic CUDA-core kernel
     assert lib.bkm_kernel_family(13, 20, 0, 2) == 1       # ... unless forced
     assert lib.bkm_kernel_family(64, 300, 0, 0) == 0      # CUDA-core path: k > 256
     assert lib.bkm_kernel_family(64, 256, 1, 0) == 0      # float64 -> CUDA cores
