@@ -299,11 +299,10 @@ def parity_check(X, labels, C_used, be, k, rows=1 << 20):
             dw = d2[bad].gather(1, want[bad][:, None])[:, 0]
             worst = max(worst, float(((dg - dw).abs() / scale).max()))
     d = int(X.shape[1])
-    tdt = torch.float32 if X.dtype != torch.float64 else torch.float64
     fam = int(be.kernel_family(d, k, X.dtype)) if hasattr(be, "kernel_family") else None
     deferred = None
-    if fam == 1:
-        dr = be.deferred_rows(n, d, k, tdt)
+    if fam in (1, 3):
+        dr = be.deferred_rows(n, d, k, X.dtype)
         deferred = None if dr is None else dr / float(n)
     return {"rows": int(rows), "mismatches": int(mism), "worst_margin": worst,
             "ok": bool(worst <= 1e-9), "deferred_frac": deferred}

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbkm_b200.so")
 
 BKM_F32 = 0
 BKM_F64 = 1
+BKM_BF16 = 2
 
 FLAG_FORCE_SIMT = 1
 FLAG_FORCE_TC = 2

@@ -24,6 +24,9 @@ if torch is not None:
         torch.float32: np.dtype("float32"), torch.float64: np.dtype("float64"),
         torch.float16: np.dtype("float16"), torch.int32: np.dtype("int32"),
         torch.int64: np.dtype("int64"), torch.bool: np.dtype("bool"),
+        # numpy has no bfloat16: a bf16 block presents itself as float32 to numpy consumers (it is widened on
+        # the way out) and stays bf16 on the device (the large-shape tensor path multiplies the rows as stored)
+        torch.bfloat16: np.dtype("float32"),
     }
 
 
@@ -33,8 +36,15 @@ def block_dtype(b):
 
 def block_to_numpy(b):
     if _is_torch(b):
-        return b.detach().cpu().numpy()
+        b = b.detach()
+        if b.dtype == torch.bfloat16:
+            b = b.float()
+        return b.cpu().numpy()
     return np.asarray(b)
+
+
+def is_bf16_block(b):
+    return _is_torch(b) and b.dtype == torch.bfloat16
 
 
 class ChunkedArray(object):
@@ -98,7 +108,7 @@ class ChunkedArray(object):
         out = []
         for b in self.blocks:
             if _is_torch(b):
-                tdt = {v: k for k, v in _TORCH_TO_NP.items()}[dtype]
+                tdt = {v: k for k, v in _TORCH_TO_NP.items() if k != torch.bfloat16}[dtype]
                 out.append(b.to(tdt))
             else:
                 out.append(np.asarray(b).astype(dtype))

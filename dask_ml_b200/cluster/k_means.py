@@ -57,14 +57,19 @@ def _to_device_data(X, backend=None, comm=None, check_finite=True):
         return X
     backend = backend or _get_backend()
     blocks = _to_blocks(X)
-    dt = _block_np_dtype(blocks[0])
-    if dt == np.dtype("int32") or dt == np.dtype("float16"):
-        dt = np.dtype("float32")            # k_means.py:171-172
-    elif dt == np.dtype("int64"):
-        dt = np.dtype("float64")            # k_means.py:173-174
-    elif dt not in (np.dtype("float32"), np.dtype("float64")):
-        dt = np.dtype("float64")
-    tdt = _NP_TO_TORCH[dt]
+    from ..chunked import is_bf16_block
+
+    if all(is_bf16_block(b) for b in blocks):
+        tdt = torch.bfloat16                # engine extension: bf16 rows stay bf16 (BASELINE config C5)
+    else:
+        dt = _block_np_dtype(blocks[0])
+        if dt == np.dtype("int32") or dt == np.dtype("float16"):
+            dt = np.dtype("float32")            # k_means.py:171-172
+        elif dt == np.dtype("int64"):
+            dt = np.dtype("float64")            # k_means.py:173-174
+        elif dt not in (np.dtype("float32"), np.dtype("float64")):
+            dt = np.dtype("float64")
+        tdt = _NP_TO_TORCH[dt]
     chunks = [backend.to_device(b, tdt) for b in blocks]
     data = DeviceData(chunks, backend, comm)
     if check_finite:
@@ -329,7 +334,7 @@ class _AssignPass(object):
         for x in X.chunks:
             n = x.shape[0]
             lab = be.empty((n,), torch.int32) if want_labels else None
-            mn = be.empty((n,), X.dtype) if want_min else None
+            mn = be.empty((n,), X.out_dtype) if want_min else None
             be.assign_chunk(x, pack, k, lab, mn, squared, acc)
             labels.append(lab)
             mins.append(mn)

@@ -35,9 +35,15 @@ static int sm_count_of_current(int* out) {
 //   second_best - best <= tau * (||x||^2 + max_j ||c_j||^2).
 // fp32 dot products of length d carry a rounding error of about sqrt(d)*2^-24 relative to
 // sum|x_i c_i| <= (||x||^2+||c||^2)/2; both distances and the -2 factor give the constant.
+static bool dtype_ok(int x_dtype) { return x_dtype == BKM_F32 || x_dtype == BKM_F64 || x_dtype == BKM_BF16; }
+
 static float tau_for(int d, int dtype, int flags, int family) {
-  if (dtype != BKM_F32 || (flags & BKM_FLAG_NO_RECHECK)) return 0.f;
+  if (dtype == BKM_F64 || (flags & BKM_FLAG_NO_RECHECK)) return 0.f;
   const float eps = 1.0f / 16777216.0f;   // 2^-24
+  // large-shape tensor path: bf16 rows are exact operands; the centres are a bf16 (hi, lo) pair: |c - hi - lo| <= 2^-18 |c|,
+  // so |sum x_i r_i| <= 2^-19 (||x||^2 + ||c||^2), doubled by the -2 factor and again for the difference of two
+  // distances: 2^-17.  To that the fp32 accumulation of 2 products per 16-element K-step (same model as family 1).
+  if (family == 3) return 1.0f / 131072.0f + (8.0f * sqrtf(2.0f * (float)((d + 7) / 8)) + 16.0f) * eps;
   // tcgen05 path (split-fp16 triple, scaled by a power of two): error sources relative to ||x||^2+||c||^2 are the
   // fp16 (hi, lo) representation of both operands (2^-22 each; 2^-25 absolute in scaled units when lo falls into
   // fp16's subnormals, negligible because the scale puts max|c| at 2^9..2^10), the dropped lo*lo term (2^-24),
@@ -55,7 +61,7 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
                         bool mstep, double* sums, long long* counts, double* dist_sum,
                         void* ws, size_t ws_bytes, int flags, cudaStream_t s) {
   if (n < 0 || d <= 0 || k <= 0 || ldx < d) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   if (!pack || !ws) return BKM_EINVAL;
   if (mstep && (!sums || !counts)) return BKM_EINVAL;
   if (n == 0) return 0;
@@ -81,12 +87,22 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   a.defer_cnt = (int*)((unsigned char*)ws + W.off_flag);
   a.defer_idx = (int*)((unsigned char*)ws + W.off_defer);
   a.out_sums = sums; a.out_counts = counts; a.out_dist_sum = dist_sum;
+  a.rec = reinterpret_cast<float4*>((unsigned char*)ws + W.off_rec);
 
   int family = bkm_kernel_family(d, k, x_dtype, flags);
   if (family < 0) return family;
   a.tau = tau_for(d, x_dtype, flags, family);
   int grid = 0;
   rc = BKM_EALIGN;
+  if (family == 3) {
+    // large-shape tensor path: E-step kernel (+ slice combine + float64 re-check), then label-indexed row passes
+    if (!a.labels) a.labels = (int*)((unsigned char*)ws + W.off_lab);
+    int parts = 0;
+    rc = launch_tc2(a, mstep, sm, &parts, s);
+    if (rc) return rc;                                  // bf16 rows have no CUDA-core fallback (BKM_EALIGN: 16-byte rows)
+    const int mparts = parts & 0xffff, dparts = parts >> 16;
+    return launch_reduce_partials(a, mparts, mparts, dparts, mstep, x_dtype, sums, counts, dist_sum, s);
+  }
   if (family == 1) {
     rc = launch_tc(a, mstep, sm, &grid, s);
     if (rc == BKM_EALIGN && !(flags & BKM_FLAG_FORCE_TC)) {   // TMA needs 16-byte aligned rows
@@ -103,7 +119,9 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   }
   if (family == 0) rc = launch_simt(a, mstep, x_dtype, sm, &grid, s);
   if (rc) return rc;
-  return launch_reduce_partials(a, grid, mstep, x_dtype, sums, counts, dist_sum, s);
+  // grid < 0: the generic kernel ran in GLOBAL mode (sums accumulated by atomics into slot 0)
+  const int g = grid < 0 ? -grid : grid;
+  return launch_reduce_partials(a, grid < 0 ? 1 : g, g, g, mstep, x_dtype, sums, counts, dist_sum, s);
 }
 
 }  // namespace bkm
@@ -141,7 +159,8 @@ int bkm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
 
 int bkm_kernel_family(int d, int k, int x_dtype, int flags) {
   if (d <= 0 || k <= 0) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
+  if (x_dtype == BKM_BF16) return tc2_shape(d, k, x_dtype) ? 3 : BKM_EUNSUPPORTED;     // bf16 rows: tensor path only
   bool tc = tc_supported(d, k, x_dtype);
   if (flags & BKM_FLAG_FORCE_SIMT) return 0;
   if (flags & BKM_FLAG_FORCE_TC) return tc ? 1 : BKM_EUNSUPPORTED;
@@ -153,7 +172,7 @@ int bkm_kernel_family(int d, int k, int x_dtype, int flags) {
 
 int bkm_centers_pack_bytes(int k, int d, int x_dtype, size_t* out) {
   if (k <= 0 || d <= 0 || !out) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   *out = pack_layout(k, d, x_dtype).total;
   return 0;
 }
@@ -161,7 +180,7 @@ int bkm_centers_pack_bytes(int k, int d, int x_dtype, size_t* out) {
 int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype, void* pack,
                      size_t pack_bytes, void* stream) {
   if (!centers64 || !pack || k <= 0 || d <= 0) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   if (pack_bytes < pack_layout(k, d, x_dtype).total) return BKM_EWORKSPACE;
   if ((uintptr_t)pack & 255) return BKM_EALIGN;
   return launch_pack(centers64, k, d, x_dtype, pack, (cudaStream_t)stream);
@@ -169,7 +188,7 @@ int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype, void* p
 
 int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out) {
   if (k <= 0 || d <= 0 || n < 0 || !out) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   int sm = 0;
   if (sm_count_of_current(&sm)) sm = kDefaultSMs;       // no device (CPU-side sizing): the B200 figure
   *out = ws_layout(n, d, k, x_dtype, sm).total;
@@ -225,7 +244,7 @@ int bkm_finalize(const double* sums, const int64_t* counts, const double* center
 int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, int* flag,
                      void* stream) {
   if (n < 0 || d <= 0 || ldx < d || !flag) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   if (n == 0) return 0;
   if (!X) return BKM_EINVAL;
   int sm = 0;
@@ -242,7 +261,7 @@ void bkm_debug_reset(void) { bkm::tc_abort_reset(); }
 
 int bkm_debug_deferred_rows(const void* workspace, int64_t n, int d, int k, int x_dtype, int* count_host) {
   if (!workspace || !count_host || n < 0 || d <= 0 || k <= 0) return BKM_EINVAL;
-  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   int sm = 0;
   if (sm_count_of_current(&sm)) sm = kDefaultSMs;
   WsLayout W = ws_layout(n, d, k, x_dtype, sm);

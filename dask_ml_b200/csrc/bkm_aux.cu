@@ -3,6 +3,7 @@
 #include "bkm_common.cuh"
 #include <math_constants.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <atomic>
 
 namespace bkm {
@@ -28,7 +29,7 @@ __global__ void pack_centers_kernel(const double* __restrict__ C, unsigned char*
   const int nth = gridDim.x * blockDim.x;
   double* c64 = reinterpret_cast<double*>(pack + L.off_c64);
   for (int i = tid; i < k * d; i += nth) c64[i] = C[i];
-  if (L.dtype == BKM_F32) {
+  if (L.dtype != BKM_F64) {
     float* cT = reinterpret_cast<float*>(pack + L.off_cT);
     for (int i = tid; i < k * L.d4; i += nth) {
       int r = i / L.d4, c = i - r * L.d4;
@@ -76,10 +77,10 @@ __global__ void pack_norms_kernel(const double* __restrict__ C, unsigned char* p
     if (lane == 0) {
       if (j < k) {
         cn64[j] = s;
-        if (L.dtype == BKM_F32) reinterpret_cast<float*>(pack + L.off_cnT)[j] = (float)s;
+        if (L.dtype != BKM_F64) reinterpret_cast<float*>(pack + L.off_cnT)[j] = (float)s;
         else reinterpret_cast<double*>(pack + L.off_cnT)[j] = s;
       }
-      if (L.dtype == BKM_F32) {
+      if (L.dtype != BKM_F64) {
         cn32[j] = j < k ? (float)s : CUDART_INF_F;
         // ||c_j||^2 as a K=8 tf32 operand row [hi, mid, lo, 0...] (hi+mid+lo == fp32 value exactly) in the
         // canonical no-swizzle K-major layout: 8-row groups of 256 B = [8 rows x 16 B | 8 rows x 16 B].
@@ -187,7 +188,7 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
   double* c64 = reinterpret_cast<double*>(pack + L.off_c64);
   for (int i = gt; i < k * d; i += nth) c64[i] = C[i];
   double* cn64 = reinterpret_cast<double*>(pack + L.off_cn64);
-  if (L.dtype == BKM_F32) {
+  if (L.dtype != BKM_F64) {
     float* cT = reinterpret_cast<float*>(pack + L.off_cT);
     for (int i = gt; i < k * L.d4; i += nth) {
       int r = i / L.d4, c = i - r * L.d4;
@@ -241,6 +242,56 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
   }
 }
 
+// Layouts of the large-shape tensor path (bkm_tc2.cu), written after the float64 norms:
+//   b2hi / b2lo [kp2][dk2] bf16: rn(-2 c), rn(-2 c - hi)          (row j = centre j; rows >= k and columns >= d: zero)
+//   bcn2 [kp2] rows [hi, mid, lo, 0 | 0 0 0 0] tf32 of ||c_j||^2 in the no-swizzle K-major operand layout; rows >= k: 3e38
+//   c64T2 [d][kp2] float64 (re-check)
+__global__ void pack_tc2_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L, Tc2Geom g) {
+  const int k = L.k, d = L.d;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const double* cn64 = reinterpret_cast<const double*>(pack + L.off_cn64);
+  __nv_bfloat16* bhi = reinterpret_cast<__nv_bfloat16*>(pack + L.off_b2hi);
+  __nv_bfloat16* blo = reinterpret_cast<__nv_bfloat16*>(pack + L.off_b2lo);
+  for (int i = gt; i < g.kp2 * g.dk2; i += nth) {
+    const int r = i / g.dk2, c = i - r * g.dk2;
+    __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+    if (r < k && c < d) {
+      const double v = -2.0 * C[(size_t)r * d + c];
+      hi = __double2bfloat16(v);
+      lo = __double2bfloat16(v - (double)__bfloat162float(hi));
+    }
+    bhi[i] = hi; blo[i] = lo;
+  }
+  for (int j = gt; j < g.kp2; j += nth) {
+    float* bcn = reinterpret_cast<float*>(pack + L.off_bcn2) + (j >> 3) * 64 + (j & 7) * 4;
+    float hi = 3.0e38f, mid = 0.f, lo = 0.f;
+    if (j < k) {
+      const float cf = (float)cn64[j];
+      hi = to_tf32_rna(cf);
+      const float r1 = cf - hi;
+      mid = to_tf32_rna(r1);
+      lo = r1 - mid;
+    }
+    bcn[0] = hi; bcn[1] = mid; bcn[2] = lo; bcn[3] = 0.f;
+    bcn[32] = 0.f; bcn[33] = 0.f; bcn[34] = 0.f; bcn[35] = 0.f;
+  }
+  double* cTT = reinterpret_cast<double*>(pack + L.off_c64T2);
+  for (int i = gt; i < d * g.kp2; i += nth) {
+    const int f = i / g.kp2, j = i - f * g.kp2;
+    cTT[i] = j < k ? C[(size_t)j * d + f] : 0.0;
+  }
+}
+
+static int launch_pack_tc2(const double* C, const PackLayout& L, void* pack, cudaStream_t s) {
+  if (!tc2_shape(L.d, L.k, L.dtype)) return 0;
+  const Tc2Geom g = tc2_geom(L.k, L.d);
+  int nb = (g.kp2 * g.dk2 + 1023) / 1024; if (nb > 296) nb = 296; if (nb < 1) nb = 1;
+  pack_tc2_kernel<<<nb, 256, 0, s>>>(C, (unsigned char*)pack, L, g);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s) {
   PackLayout L = pack_layout(k, d, dtype);
   if (k <= 2048 && (long long)k * d <= 65536) {
@@ -248,7 +299,7 @@ int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream
     pack_fused_kernel<<<nb, 1024, (size_t)k * 8, s>>>(C, (unsigned char*)pack, L);
     note_launch();
     BKM_CUDA_TRY(cudaGetLastError());
-    return 0;
+    return launch_pack_tc2(C, L, pack, s);
   }
   int nb = (L.kp * L.dk + 255) / 256; if (nb > 296) nb = 296; if (nb < 1) nb = 1;
   pack_scale_kernel<<<1, 1024, 0, s>>>(C, (unsigned char*)pack, L);
@@ -258,7 +309,7 @@ int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream
   pack_header_kernel<<<1, 256, 0, s>>>((unsigned char*)pack, L);
   note_launch(4);
   BKM_CUDA_TRY(cudaGetLastError());
-  return 0;
+  return launch_pack_tc2(C, L, pack, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -267,7 +318,7 @@ int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream
 // ---------------------------------------------------------------------------------------
 template <typename PS>
 __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* __restrict__ pcnt,
-                                       const double* __restrict__ pin, int grid, int sum_parts,
+                                       const double* __restrict__ pin, int cnt_parts, int pin_parts, int sum_parts,
                                        int kd, int k, bool mstep,
                                        double* sums, long long* counts, double* dist_sum) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,39 +343,39 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
     for (int i = nth - 1 - tid; i < k; i += nth) {
       long long c = 0;
       int g = 0;
-      for (; g + 16 <= grid; g += 16) {
+      for (; g + 16 <= cnt_parts; g += 16) {
         int v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = pcnt[(size_t)(g + q) * k + i];
 #pragma unroll
         for (int q = 0; q < 16; ++q) c += v[q];
       }
-      for (; g < grid; ++g) c += pcnt[(size_t)g * k + i];
+      for (; g < cnt_parts; ++g) c += pcnt[(size_t)g * k + i];
       counts[i] += c;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32 && dist_sum) {
     // lane l adds CTAs l, l+32, ... in order, then a fixed shuffle tree: reproducible
     double s = 0.0;
-    for (int g = threadIdx.x; g < grid; g += 32) s += pin[g];
+    for (int g = threadIdx.x; g < pin_parts; g += 32) s += pin[g];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (threadIdx.x == 0) *dist_sum += s;
   }
 }
 
-int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
+// sum_parts / cnt_parts / pin_parts: how many partial slots the chunk kernel(s) wrote of the sums, the counts and the
+// distance sums (one per CTA for the fused kernels; 1 sums slot in the generic kernel's GLOBAL mode; row blocks and
+// distance-pass CTAs for the large-shape path)
+int launch_reduce_partials(const ChunkArgs& a, int sum_parts, int cnt_parts, int pin_parts, bool mstep, int dtype,
                            double* sums, long long* counts, double* dist_sum, cudaStream_t s) {
-  // grid < 0 : the kernel ran in GLOBAL mode (sums accumulated by atomics into slot 0)
-  int sum_parts = grid < 0 ? 1 : grid;
-  if (grid < 0) grid = -grid;
   const int kd = a.k * a.d;
   int nb = (kd + 255) / 256; if (nb > 148) nb = 148; if (nb < 1) nb = 1;
-  if (dtype == BKM_F32)
-    reduce_partials_kernel<float><<<nb, 256, 0, s>>>((const float*)a.psum, a.pcnt, a.pin, grid, sum_parts,
+  if (dtype != BKM_F64)
+    reduce_partials_kernel<float><<<nb, 256, 0, s>>>((const float*)a.psum, a.pcnt, a.pin, cnt_parts, pin_parts, sum_parts,
                                                      kd, a.k, mstep, sums, counts, dist_sum);
   else
-    reduce_partials_kernel<double><<<nb, 256, 0, s>>>((const double*)a.psum, a.pcnt, a.pin, grid, sum_parts,
+    reduce_partials_kernel<double><<<nb, 256, 0, s>>>((const double*)a.psum, a.pcnt, a.pin, cnt_parts, pin_parts, sum_parts,
                                                       kd, a.k, mstep, sums, counts, dist_sum);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
@@ -507,6 +558,9 @@ int launch_transform(const void* X, long long n, int d, long long ldx, int dtype
 // ---------------------------------------------------------------------------------------
 // NaN / inf scan (k_means.py:179-180)
 // ---------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ double cf_to_double(T v) { return (double)v; }
+template <> __device__ __forceinline__ double cf_to_double<__nv_bfloat16>(__nv_bfloat16 v) { return (double)__bfloat162float(v); }
+
 template <typename T>
 __global__ void check_finite_kernel(const T* __restrict__ X, long long n, int d, long long ldx, int* flag) {
   bool bad = false;
@@ -515,13 +569,13 @@ __global__ void check_finite_kernel(const T* __restrict__ X, long long n, int d,
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot;
          i += (long long)gridDim.x * blockDim.x) {
       T v = X[i];
-      bad |= !(fabs((double)v) <= 1.7976931348623157e308);
+      bad |= !(fabs(cf_to_double<T>(v)) <= 1.7976931348623157e308);
     }
   } else {
     for (long long r = blockIdx.x; r < n; r += gridDim.x)
       for (int c = threadIdx.x; c < d; c += blockDim.x) {
         T v = X[r * ldx + c];
-        bad |= !(fabs((double)v) <= 1.7976931348623157e308);
+        bad |= !(fabs(cf_to_double<T>(v)) <= 1.7976931348623157e308);
       }
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
@@ -532,6 +586,7 @@ int launch_check_finite(const void* X, long long n, int d, long long ldx, int dt
   if (n == 0) return 0;
   int grid = sm_count * 8;
   if (dtype == BKM_F32) check_finite_kernel<float><<<grid, 256, 0, s>>>((const float*)X, n, d, ldx, flag);
+  else if (dtype == BKM_BF16) check_finite_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)X, n, d, ldx, flag);
   else check_finite_kernel<double><<<grid, 256, 0, s>>>((const double*)X, n, d, ldx, flag);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());

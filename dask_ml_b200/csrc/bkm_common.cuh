@@ -21,6 +21,34 @@ inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_r
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------
+// Geometry of the large-shape tensor path (bkm_tc2.cu): the k centres are cut into S slices of NS <= 256 (one slice
+// per CTA, resident in shared memory), the features into KB blocks of 64 16-bit values (one 128-byte swizzle atom).
+// The label-indexed row pass (bkm_rowpass.cu) cuts the features into DS slices of FS so that k*FS fp32 sums fit one CTA.
+// ---------------------------------------------------------------------------------------
+struct Tc2Geom { int S, NS, KB, kp2, dk2, FS, DS; };
+static inline Tc2Geom tc2_geom(int k, int d) {
+  Tc2Geom g;
+  g.S = (k + 255) / 256;
+  const int per = (k + g.S - 1) / g.S;
+  g.NS = (per + 15) / 16 * 16;
+  g.kp2 = g.S * g.NS;
+  g.KB = (d + 63) / 64;
+  g.dk2 = g.KB * 64;
+  int fs = 128;
+  while (fs > 8 && (size_t)k * fs * 4 > 160 * 1024) fs >>= 1;
+  int dpow = 8;
+  while (dpow < d) dpow <<= 1;
+  if (fs > dpow) fs = dpow;
+  g.FS = fs;
+  g.DS = (d + fs - 1) / fs;
+  return g;
+}
+// bf16 input of any k / d <= 128 (BASELINE config C5: 128 features, k = 1024)
+static inline bool tc2_shape(int d, int k, int dtype) {
+  return dtype == BKM_BF16 && d >= 1 && d <= 128 && k >= 1 && k <= 4096;     // k * 8 features * 4 B <= 160 KB
+}
+
+// ---------------------------------------------------------------------------------------
 // Centre pack: one device buffer holding every layout of the (k,d) centres the kernels use.
 // Built by pack_centers_kernel from the float64 centres (reference keeps centres in f64:
 // dask_ml/cluster/k_means.py:551-552).
@@ -33,6 +61,9 @@ struct PackLayout {
   int dh;      // row length of the fp16 MMA operand tiles: 64 halves = one 128-byte swizzle atom (d <= 64)
   size_t esz;  // sizeof(T)
   size_t off_cT, off_cnT, off_c64, off_cn64, off_bhi, off_blo, off_cn32, off_bcn, off_c64T, total;
+  // large-shape tensor path (tc2_shape): fp16 (hi, lo) operand tiles [kp2][dk2], ||c||^2 operand rows [kp2][8] tf32,
+  // float64 centres transposed [d][kp2]
+  size_t off_b2hi, off_b2lo, off_bcn2, off_c64T2;
 };
 
 static inline PackLayout pack_layout(int k, int d, int dtype) {
@@ -42,7 +73,7 @@ static inline PackLayout pack_layout(int k, int d, int dtype) {
   L.kp = (k + 15) / 16 * 16;
   L.dk = (d + 31) / 32 * 32;
   L.dh = 64;
-  L.esz = dtype == BKM_F64 ? 8 : 4;
+  L.esz = dtype == BKM_F64 ? 8 : 4;                // bf16 input: the fp32 layouts (the kernels widen the rows)
   size_t o = 256;  // header
   L.off_cT = o;   o = align_up(o + (size_t)k * L.d4 * L.esz, 256);
   L.off_cnT = o;  o = align_up(o + (size_t)k * L.esz, 256);
@@ -54,6 +85,14 @@ static inline PackLayout pack_layout(int k, int d, int dtype) {
   L.off_bcn = o;  o = align_up(o + (size_t)L.kp * 32, 256);   // ||c||^2 as an MMA operand tile (see bkm_tc.cu)
   // float64 centres transposed [d][kp] for the float64 re-check of the tensor path (coalesced over centres)
   L.off_c64T = o; if (dtype == BKM_F32 && d <= 64 && k <= 256) o = align_up(o + (size_t)d * L.kp * 8, 256);
+  L.off_b2hi = L.off_b2lo = L.off_bcn2 = L.off_c64T2 = o;
+  if (tc2_shape(d, k, dtype)) {
+    const Tc2Geom g = tc2_geom(k, d);
+    L.off_b2hi = o;  o = align_up(o + (size_t)g.kp2 * g.dk2 * 2, 1024);
+    L.off_b2lo = o;  o = align_up(o + (size_t)g.kp2 * g.dk2 * 2, 1024);
+    L.off_bcn2 = o;  o = align_up(o + (size_t)g.kp2 * 32, 256);
+    L.off_c64T2 = o; o = align_up(o + (size_t)d * g.kp2 * 8, 256);
+  }
   L.total = o;
   return L;
 }
@@ -75,7 +114,7 @@ struct PackHeader {
 static const int kDefaultSMs = 148;
 
 struct WsLayout {
-  size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, total;
+  size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, off_rec, off_lab, total;
   size_t psum_esz;
   int psum_slots;     // capacity of off_psum in [k*d] slots
   int part_slots;     // capacity of off_pcnt / off_pin (per-CTA counts / distance sums): the largest grid
@@ -86,7 +125,12 @@ static inline WsLayout ws_layout(long long n, int d, int k, int dtype, int sm_co
   W.psum_esz = dtype == BKM_F64 ? 8 : 4;
   const size_t slot = (size_t)k * d * W.psum_esz;
   W.part_slots = sm_count * 8;
-  if (2 * slot > 227 * 1024) W.psum_slots = 1;                 // cannot be CTA-resident: global accumulation
+  const bool tc2 = tc2_shape(d, k, dtype);
+  if (tc2) {
+    // label-indexed row pass: one [k][d] slot per row block (sm_count / DS CTAs own the same row block)
+    const Tc2Geom g = tc2_geom(k, d);
+    W.psum_slots = sm_count / g.DS > 0 ? sm_count / g.DS : 1;
+  } else if (2 * slot > 227 * 1024) W.psum_slots = 1;          // cannot be CTA-resident: global accumulation
   else {
     size_t per_sm = (227 * 1024) / (2 * slot);                  // CTAs per SM that could hold centres + sums
     if (per_sm > 8) per_sm = 8;
@@ -99,6 +143,12 @@ static inline WsLayout ws_layout(long long n, int d, int k, int dtype, int sm_co
   W.off_pin = o;  o = align_up(o + (size_t)W.part_slots * 8, 256);
   W.off_flag = o; o = align_up(o + 256, 256);          // [0] = deferred-row counter
   W.off_defer = o; o = align_up(o + (size_t)(n > 0 ? n : 0) * 4, 256);
+  // large-shape tensor path with more than one centre slice: per (slice, row) partial arg-min records (16 B)
+  W.off_rec = o;
+  if (tc2 && tc2_geom(k, d).S > 1) o = align_up(o + (size_t)tc2_geom(k, d).S * (size_t)(n > 0 ? n : 0) * 16, 256);
+  // ... and a label buffer for callers that do not want the labels (the row passes are driven by them)
+  W.off_lab = o;
+  if (tc2) o = align_up(o + (size_t)(n > 0 ? n : 0) * 4, 256);
   W.total = o;
   return W;
 }
@@ -124,6 +174,7 @@ struct ChunkArgs {
   int* defer_idx;     // [n] their row indices
   int psum_slots;     // capacity of psum in [k*d] slots (grid clamp of the kernels that keep per-CTA sums)
   int part_slots;     // capacity of pcnt / pin
+  float4* rec;        // large-shape tensor path: [S][n] partial arg-min records {m1, m2, label bits, ||x||^2}
   double* out_sums;   // final accumulators (the re-check kernel adds the deferred rows' contributions)
   long long* out_counts;
   double* out_dist_sum;
@@ -138,8 +189,12 @@ int tc_trace(long long* out, int n);
 // implemented in bkm_stream.cu
 bool stream_supported(int d, int k, int dtype);
 int launch_stream(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
+// implemented in bkm_tc2.cu / bkm_rowpass.cu
+int launch_tc2(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
+int launch_rowpass_mstep(const ChunkArgs& a, int x_dtype, int sm_count, int* parts_out, cudaStream_t s);
+int launch_rowpass_dist(const ChunkArgs& a, int x_dtype, int sm_count, int* parts_out, cudaStream_t s);
 // implemented in bkm_aux.cu
-int launch_reduce_partials(const ChunkArgs& a, int grid, bool mstep, int dtype,
+int launch_reduce_partials(const ChunkArgs& a, int sum_parts, int cnt_parts, int pin_parts, bool mstep, int dtype,
                            double* sums, long long* counts, double* dist_sum, cudaStream_t s);
 
 }  // namespace bkm

@@ -19,7 +19,12 @@ from . import _lib
 from .chunked import ChunkedArray, block_dtype, _is_torch
 
 _NP_TO_TORCH = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64}
-_DT_CODE = {torch.float32: _lib.BKM_F32, torch.float64: _lib.BKM_F64}
+_DT_CODE = {torch.float32: _lib.BKM_F32, torch.float64: _lib.BKM_F64, torch.bfloat16: _lib.BKM_BF16}
+
+
+def out_dtype(x_dtype):
+    """dtype of the per-row distance outputs for rows of ``x_dtype`` (bf16 rows give float32 distances)."""
+    return torch.float32 if x_dtype == torch.bfloat16 else x_dtype
 
 
 def dist_info():
@@ -67,6 +72,7 @@ class CudaBackend(object):
     """Calls the sm_100a kernels through the C ABI.  Fails loudly without a GPU/library."""
 
     name = "b200"
+    supports_bf16 = True          # bfloat16 rows: large-shape tensor path (bkm_tc2.cu), d <= 128
 
     def __init__(self, device=None, flags=0):
         if not torch.cuda.is_available():
@@ -138,6 +144,14 @@ class CudaBackend(object):
                 a = a.copy()                 # torch refuses read-only buffers
             t = torch.from_numpy(a)
         t = t.to(device=self.device, dtype=dtype, non_blocking=True)
+        if t.dim() == 2 and dtype == torch.bfloat16 and t.shape[0] > 0 and (t.shape[1] % 8 or t.stride(0) % 8 or t.stride(1) != 1):
+            # bf16 rows are read by TMA: 16-byte row pitch = a multiple of 8 elements (zero padded view)
+            n, d = t.shape
+            buf = torch.zeros((n, (d + 7) // 8 * 8), dtype=dtype, device=self.device)
+            buf[:, :d] = t
+            return buf[:, :d]
+        if t.dim() == 2 and dtype == torch.bfloat16:
+            return t
         if t.dim() == 2 and dtype == torch.float32 and t.shape[1] % 4 and t.shape[1] <= 64 and t.shape[0] > 0:
             # The tensor path reads row tiles with TMA, which needs a 16-byte row pitch: rows are stored with the
             # pitch rounded up to 4 floats (zero padded) and handed on as a (n, d) view of that buffer.
@@ -234,7 +248,12 @@ class DeviceData(object):
 
     @property
     def np_dtype(self):
-        return np.dtype("float32") if self.dtype == torch.float32 else np.dtype("float64")
+        """dtype of host-side results (cluster_centers_): that of X; float32 for bfloat16 rows (numpy has no bf16)."""
+        return np.dtype("float64") if self.dtype == torch.float64 else np.dtype("float32")
+
+    @property
+    def out_dtype(self):
+        return out_dtype(self.dtype)
 
     def local_rows(self, local_idx):
         """Rows by LOCAL index -> numpy (len, d)."""
@@ -245,7 +264,8 @@ class DeviceData(object):
         for w in np.unique(which):
             pos = np.nonzero(which == w)[0]
             rel = torch.as_tensor(local_idx[pos] - self.chunk_offsets[w], dtype=torch.int64, device=self.chunks[w].device)
-            out[pos] = self.chunks[w].index_select(0, rel).cpu().numpy()
+            sel = self.chunks[w].index_select(0, rel)
+            out[pos] = (sel.float() if sel.dtype == torch.bfloat16 else sel).cpu().numpy()
         return out
 
     def global_rows(self, global_idx):
@@ -264,4 +284,4 @@ class DeviceData(object):
 
     def to_host(self):
         """All LOCAL rows as one numpy array (used only by the in-memory k-means++ init)."""
-        return np.concatenate([c.cpu().numpy() for c in self.chunks], axis=0)
+        return np.concatenate([(c.float() if c.dtype == torch.bfloat16 else c).cpu().numpy() for c in self.chunks], axis=0)

@@ -42,7 +42,7 @@ def pairwise_distances_argmin_min(X, Y, axis=1, metric="euclidean", batch_size=N
     for x in X.chunks:
         n = int(x.shape[0])
         lab = be.empty((n,), torch.int32)
-        mn = be.empty((n,), X.dtype)
+        mn = be.empty((n,), X.out_dtype)
         be.assign_chunk(x, pack, k, lab, mn, squared, acc)
         argmins.append(lab.to(torch.int64))
         mins.append(mn.to(torch.float64))
@@ -70,6 +70,11 @@ def euclidean_distances(X, Y=None, Y_norm_squared=None, squared=False, X_norm_sq
 
     X = _to_device_data(X, check_finite=False)
     Y = np.asarray(Y)
+    if X.dtype == torch.bfloat16:
+        # the full distance matrix of bf16 rows is produced in float32 (no bf16 transform kernel)
+        from ..engine import DeviceData
+
+        X = DeviceData([c.to(torch.float32) for c in X.chunks], X.backend, X.comm)
     if X.dtype == torch.float32 and Y.dtype == np.float64:
         # result dtype follows numpy promotion of (X, Y) like -2*dot(X, Y.T)+XX+YY in the reference
         from ..engine import DeviceData

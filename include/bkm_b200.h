@@ -45,6 +45,7 @@ extern "C" {
 /* element types of X */
 #define BKM_F32 0
 #define BKM_F64 1
+#define BKM_BF16 2   /* bfloat16 rows (16-byte row pitch); distances / min_d2 outputs are float32 */
 
 /* error codes (negative) */
 #define BKM_OK            0

@@ -324,3 +324,129 @@ def test_tcgen05_odd_feature_counts(be, oracle, n, d, k):
     exact = ((x.double() - C[got]) ** 2).sum(1)
     scale = (x.double() ** 2).sum(1) + (C ** 2).sum(1).max()
     assert float(((md.double() - exact).abs() / scale).max()) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ streaming kernel (family 2)
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 255, 256, 257, 4097, 148 * 8 * 32 * 3 + 5, 1_000_003])
+@pytest.mark.parametrize("d,k,pitch", [(13, 20, 13), (13, 20, 16), (13, 20, 14), (16, 31, 16), (1, 2, 1), (3, 5, 3),
+                                       (7, 1, 7), (9, 31, 12), (5, 8, 24)])
+def test_stream_kernel_tails(be, n, d, k, pitch):
+    """Family 2 (bkm_stream.cu): every tail of the per-warp ring (fewer tiles than warps, a partial last tile, rows with
+    and without a padded pitch), all entry points, against the float64 arg-min evaluated on the device."""
+    import torch
+
+    assert be.kernel_family(d, k, torch.float32) == 2
+    g = torch.Generator(device=be.device).manual_seed(n * 31 + d * 7 + k)
+    cent = torch.empty((max(2, k // 2), d), device=be.device).uniform_(-10, 10, generator=g)
+    Xc = cent[torch.randint(0, cent.shape[0], (n,), device=be.device, generator=g)] + \
+        torch.randn((n, d), device=be.device, generator=g)
+    if pitch != d:
+        buf = torch.full((n, pitch), 7.5e4, device=be.device)       # the padding must never leak into a result
+        buf[:, :d] = Xc
+        X = buf[:, :d]
+    else:
+        X = Xc.contiguous()
+    C = Xc[torch.randint(0, n, (k,), device=be.device, generator=g)].double() + \
+        0.01 * torch.randn((k, d), device=be.device, generator=g, dtype=torch.float64)
+    pack = be.pack_centers(C.contiguous(), torch.float32)
+    labels = be.empty((n,), torch.int32)
+    mind2 = be.empty((n,), torch.float32)
+    sums = be.zeros((k * d,), torch.float64)
+    counts = be.zeros((k,), torch.int64)
+    inertia = be.zeros((1,), torch.float64)
+    be.lloyd_chunk(X, pack, k, labels, mind2, sums, counts, inertia)
+    torch.cuda.synchronize()
+    want, margin = _exact_labels_f64(Xc, C)
+    got = labels.long()
+    bad = got != want
+    if bool(bad.any()):
+        xs = (Xc.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
+        assert bool((margin[bad] <= 1e-9 * xs).all()), int(bad.sum())
+    assert torch.equal(counts, torch.bincount(got, minlength=k))
+    ref = torch.zeros((k, d), dtype=torch.float64, device=be.device).index_add_(0, got, Xc.double())
+    assert float((sums.view(k, d) - ref).abs().max()) <= 2e-6 * float(ref.abs().max()) + 1e-9
+    exact = ((Xc.double() - C[got]) ** 2).sum(1)
+    scale = (Xc.double() ** 2).sum(1) + (C ** 2).sum(1).max()
+    assert float(((mind2.double() - exact).abs() / scale).max()) < 2e-6
+    assert abs(float(inertia[0]) - float(exact.sum())) <= 1e-5 * float(exact.sum()) + 2e-6 * float(scale.sum())
+    # assignment-only entry point (no M-step), non-squared distances
+    lab2 = be.empty((n,), torch.int32)
+    md = be.empty((n,), torch.float32)
+    ds = be.zeros((1,), torch.float64)
+    be.assign_chunk(X, pack, k, lab2, md, False, ds)
+    torch.cuda.synchronize()
+    assert torch.equal(lab2, labels)
+    assert float(((md.double() ** 2 - exact).abs() / scale).max()) < 4e-6
+    # Lloyd step without distances (what fit runs)
+    sums2 = be.zeros((k * d,), torch.float64)
+    counts2 = be.zeros((k,), torch.int64)
+    lab3 = be.empty((n,), torch.int32)
+    be.lloyd_chunk(X, pack, k, lab3, None, sums2, counts2, None)
+    torch.cuda.synchronize()
+    assert torch.equal(lab3, labels) and torch.equal(counts2, counts)
+    assert torch.equal(sums2, sums)            # bit-reproducible: fixed CTA / warp order
+
+
+def test_stream_kernel_matches_generic_kernel(be):
+    """Family 2 against the generic CUDA-core kernel (FORCE_SIMT) on badly scaled data with many near-ties."""
+    import torch
+
+    n, d, k = 200_000, 13, 20
+    g = torch.Generator(device=be.device).manual_seed(11)
+    scales = torch.logspace(0, 3, d, device=be.device)
+    X = (torch.randn((n, d), device=be.device, generator=g) * scales).contiguous()
+    C = X[:k].double().contiguous()
+    pack = be.pack_centers(C, torch.float32)
+    out = []
+    for flags in (0, 1):
+        be.flags = flags
+        labels = be.empty((n,), torch.int32)
+        sums = be.zeros((k * d,), torch.float64)
+        counts = be.zeros((k,), torch.int64)
+        be.lloyd_chunk(X, pack, k, labels, None, sums, counts, None)
+        torch.cuda.synchronize()
+        out.append((labels.clone(), sums.clone(), counts.clone()))
+    be.flags = 0
+    want, margin = _exact_labels_f64(X, C)
+    for labels, sums, counts in out:
+        bad = labels.long() != want
+        if bool(bad.any()):
+            xs = (X.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
+            assert bool((margin[bad] <= 1e-9 * xs).all()), int(bad.sum())
+    assert int((out[0][0] != out[1][0]).sum()) <= 2
+
+
+# ------------------------------------------------------------------------------------------ BASELINE sizes
+@pytest.mark.parametrize("name,n,d,k", [("C2", 10_000_000, 64, 256), ("C3", 4_898_431, 41, 100), ("C4", 15_000_000, 13, 20)])
+def test_baseline_size_parity(be, name, n, d, k):
+    """Labels, counts and sums at the FULL BASELINE.json sizes against the float64 arg-min evaluated on the device (every
+    row), plus the size-independent invariants: counts sum to n, the sums add up to the column sums of X."""
+    import torch
+    from bench import synth_config_device, synth_blobs_device
+
+    X = synth_blobs_device(n, d, k, 5, be.device, torch.float32) if name == "C2" else synth_config_device(name, n, 0, be.device)
+    x = be.to_device(X, torch.float32) if (d % 4 and be.kernel_family(d, k, torch.float32) == 1) else X
+    C = X[:k].double().contiguous()
+    pack = be.pack_centers(C, torch.float32)
+    labels = be.empty((n,), torch.int32)
+    sums = be.zeros((k * d,), torch.float64)
+    counts = be.zeros((k,), torch.int64)
+    be.lloyd_chunk(x, pack, k, labels, None, sums, counts, None)
+    torch.cuda.synchronize()
+    assert be.lib.bkm_debug_abort_code() == 0
+    got = labels.long()
+    assert int(counts.sum()) == n and torch.equal(counts, torch.bincount(got, minlength=k))
+    colsum = torch.zeros((d,), dtype=torch.float64, device=be.device)
+    for s in range(0, n, 1 << 20):
+        colsum += X[s:s + (1 << 20)].double().sum(0)
+    assert float((sums.view(k, d).sum(0) - colsum).abs().max()) <= 1e-6 * float(colsum.abs().max()) + 1e-3
+    want, margin = _exact_labels_f64(X, C)
+    bad = got != want
+    nbad = int(bad.sum())
+    if nbad:
+        xs = (X.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max()
+        assert bool((margin[bad] <= 1e-9 * xs).all()), nbad
+    assert nbad <= 1e-5 * n
+    if be.kernel_family(d, k, torch.float32) == 1:
+        # the rounding bound tau defers only a small fraction of rows to the float64 re-check
+        assert be.deferred_rows(n, d, k, torch.float32) < 0.01 * n
