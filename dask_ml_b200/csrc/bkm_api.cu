@@ -88,6 +88,8 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   a.defer_idx = (int*)((unsigned char*)ws + W.off_defer);
   a.out_sums = sums; a.out_counts = counts; a.out_dist_sum = dist_sum;
   a.rec = reinterpret_cast<float4*>((unsigned char*)ws + W.off_rec);
+  a.bin_list = (unsigned char*)ws + W.off_bin;
+  a.bin_off = (int*)((unsigned char*)ws + W.off_binoff);
 
   int family = bkm_kernel_family(d, k, x_dtype, flags);
   if (family < 0) return family;

@@ -23,9 +23,9 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // ---------------------------------------------------------------------------------------
 // Geometry of the large-shape tensor path (bkm_tc2.cu): the k centres are cut into S slices of NS <= 256 (one slice
 // per CTA, resident in shared memory), the features into KB blocks of 64 16-bit values (one 128-byte swizzle atom).
-// The label-indexed row pass (bkm_rowpass.cu) cuts the features into DS slices of FS so that k*FS fp32 sums fit one CTA.
+// The label-indexed row pass (bkm_rowpass.cu) cuts the clusters into DS slices so that (k/DS)*d fp32 sums fit one CTA.
 // ---------------------------------------------------------------------------------------
-struct Tc2Geom { int S, NS, KB, kp2, dk2, FS, DS; };
+struct Tc2Geom { int S, NS, KB, kp2, dk2, DS; };
 static inline Tc2Geom tc2_geom(int k, int d) {
   Tc2Geom g;
   g.S = (k + 255) / 256;
@@ -34,18 +34,16 @@ static inline Tc2Geom tc2_geom(int k, int d) {
   g.kp2 = g.S * g.NS;
   g.KB = (d + 63) / 64;
   g.dk2 = g.KB * 64;
-  int fs = 128;
-  while (fs > 8 && (size_t)k * fs * 4 > 160 * 1024) fs >>= 1;
-  int dpow = 8;
-  while (dpow < d) dpow <<= 1;
-  if (fs > dpow) fs = dpow;
-  g.FS = fs;
-  g.DS = (d + fs - 1) / fs;
+  // label-indexed M-step (bkm_rowpass.cu): DS cluster slices so that the (k / DS) x d_padded fp32 sums of one slice
+  // (+ counts + two staged label tiles) fit one CTA
+  const int dpad = d <= 32 ? 32 : (d <= 64 ? 64 : 128);
+  g.DS = 1;
+  while ((size_t)((k + g.DS - 1) / g.DS) * dpad * 4 + (size_t)((k + g.DS - 1) / g.DS) * 4 + 40 * 1024 > 210 * 1024) g.DS <<= 1;      // a power of two
   return g;
 }
 // bf16 input of any k / d <= 128 (BASELINE config C5: 128 features, k = 1024)
 static inline bool tc2_shape(int d, int k, int dtype) {
-  return dtype == BKM_BF16 && d >= 1 && d <= 128 && k >= 1 && k <= 4096;     // k * 8 features * 4 B <= 160 KB
+  return dtype == BKM_BF16 && d >= 1 && d <= 128 && k >= 1 && k <= 4096;      // <= 16 cluster slices in the M-step row pass
 }
 
 // ---------------------------------------------------------------------------------------
@@ -114,7 +112,7 @@ struct PackHeader {
 static const int kDefaultSMs = 148;
 
 struct WsLayout {
-  size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, off_rec, off_lab, total;
+  size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, off_rec, off_lab, off_bin, off_binoff, total;
   size_t psum_esz;
   int psum_slots;     // capacity of off_psum in [k*d] slots
   int part_slots;     // capacity of off_pcnt / off_pin (per-CTA counts / distance sums): the largest grid
@@ -149,6 +147,13 @@ static inline WsLayout ws_layout(long long n, int d, int k, int dtype, int sm_co
   // ... and a label buffer for callers that do not want the labels (the row passes are driven by them)
   W.off_lab = o;
   if (tc2) o = align_up(o + (size_t)(n > 0 ? n : 0) * 4, 256);
+  // ... and the per-tile bins of the M-step row pass: 4 B per row (tiles of 4096 rows) + 257 offsets per tile
+  W.off_bin = W.off_binoff = o;
+  if (tc2) {
+    const size_t ntile = (size_t)((n > 0 ? n : 0) + 4095) / 4096;
+    W.off_bin = o;    o = align_up(o + ntile * 4096 * 4, 256);
+    W.off_binoff = o; o = align_up(o + ntile * 257 * 4, 256);
+  }
   W.total = o;
   return W;
 }
@@ -175,6 +180,8 @@ struct ChunkArgs {
   int psum_slots;     // capacity of psum in [k*d] slots (grid clamp of the kernels that keep per-CTA sums)
   int part_slots;     // capacity of pcnt / pin
   float4* rec;        // large-shape tensor path: [S][n] partial arg-min records {m1, m2, label bits, ||x||^2}
+  void* bin_list;     // ... M-step row pass: per-tile row bins (4 B per row) and their bucket offsets
+  int* bin_off;
   double* out_sums;   // final accumulators (the re-check kernel adds the deferred rows' contributions)
   long long* out_counts;
   double* out_dist_sum;

@@ -2,10 +2,11 @@
 // tensor path, bkm_tc2.cu: BASELINE config C5, k = 1024, d = 128 -> 512 KB of fp32 sums).
 //
 //   rowpass_mstep_kernel   M-step (_centers_dense, dask_ml/cluster/k_means.py:572-582 + da.bincount :548) from the
-//                          labels the E-step wrote: the features are cut into DS slices of FS so that k x FS fp32 sums
-//                          DO fit shared memory; CTA (row block rb, feature slice ds) sweeps its rows once, reading
-//                          only its FS features of every row (whole 32-byte sectors: no HBM over-fetch), warp w owning
-//                          the clusters c % NW == w (no atomics, fixed order).  Per-row-block partials are folded in
+//                          labels the E-step wrote: the CLUSTERS are cut into DS interleaved slices so that the
+//                          (k / DS) x d fp32 sums of a slice DO fit shared memory; CTA (row block rb, cluster slice cs)
+//                          scans the labels of its rows and gathers the rows of its clusters (whole rows, coalesced:
+//                          every row of X is read once over the DS CTAs), warp w owning the local clusters
+//                          (c / DS) % NW == w (no atomics, fixed order).  Per-row-block partials are folded in
 //                          float64 by reduce_partials in row-block order.
 //   rowpass_dist_kernel    winning distance sum_i (x_i - c_label,i)^2 in direct form (fp32, no cancellation), one warp per
 //                          row: min_out and the per-CTA distance sums (inertia, k_means.py:566 / k-means|| cost :466-469).
@@ -20,105 +21,213 @@ namespace bkm {
 
 static const int RP_THREADS = 512;
 static const int RP_NW = RP_THREADS / 32;
-static const int RP_TR = 256;                 // rows per staged tile
+static const int RP_TILE = 4096;              // rows per binning tile (row offsets inside a tile take 12 bits)
+static const int RP_BATCH = 16;               // rows gathered per batch (loads in flight per warp)
+static const int RP_MAXB = 256;               // buckets = cluster slices x warps (CS <= 16)
 
 template <typename TX> __device__ __forceinline__ float rp_to_float(TX v);
 template <> __device__ __forceinline__ float rp_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float rp_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 struct RpCfg {
-  int FS, DS, RB;          // features per slice, feature slices, row blocks (grid = RB * DS)
-  uint32_t off_sums, off_cnt, off_lab, off_x, total;
-  uint32_t xrow_bytes;     // bytes of one staged row slice (FS * sizeof(TX))
+  int CS, LCS, RB, KL;     // cluster slices (a power of two, LCS = log2), row blocks (grid = RB * CS), clusters per slice
+  int NB;                  // buckets = CS * NW
+  long long ntiles, tiles_per_block;
+  uint32_t off_sums, off_cnt, total;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// FPL features per lane of a row: a warp reads a whole row with one load per lane (lane l: features l*FPL ...).
+// raw = the loaded bits (kept packed while the loads of a batch are in flight), add() widens and accumulates
+template <typename TX, int FPL> struct RowPiece;
+// (volatile asm loads: the compiler must not sink a load next to its use — the point is 16 rows in flight per warp)
+template <> struct RowPiece<__nv_bfloat16, 1> {
+  unsigned short raw;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(raw) : "l"(p)); }
+  __device__ __forceinline__ void add(float* sr) const { sr[0] += __uint_as_float((uint32_t)raw << 16); }
+};
+template <> struct RowPiece<__nv_bfloat16, 2> {
+  uint32_t raw;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(raw) : "l"(p)); }
+  __device__ __forceinline__ void add(float* sr) const {
+    float2 t = *reinterpret_cast<float2*>(sr);
+    t.x += __uint_as_float(raw << 16); t.y += __uint_as_float(raw & 0xffff0000u);
+    *reinterpret_cast<float2*>(sr) = t;
+  }
+};
+template <> struct RowPiece<__nv_bfloat16, 4> {
+  uint2 raw;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "l"(p));
+  }
+  __device__ __forceinline__ void add(float* sr) const {
+    float4 t = *reinterpret_cast<float4*>(sr);             // one 16-byte access per lane: conflict-free
+    t.x += __uint_as_float(raw.x << 16); t.y += __uint_as_float(raw.x & 0xffff0000u);
+    t.z += __uint_as_float(raw.y << 16); t.w += __uint_as_float(raw.y & 0xffff0000u);
+    *reinterpret_cast<float4*>(sr) = t;
+  }
+};
 
-template <typename TX>
+// ------------------------------------------------------------------------------------------
+// Step 1: bin the rows of every 4096-row tile by bucket = (cluster slice, owner warp) of their label — a stable
+// counting sort per tile (rows of a bucket stay in row order, so the sums are reproducible).  bins[tile*4096 + pos]
+// = row-in-tile | local cluster << 12; tile_off[tile][b] = first position of bucket b, [NB] = valid rows of the tile.
+// One CTA per tile (grid-stride); labels are read once.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RP_THREADS)
+rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigned* __restrict__ bins, int* __restrict__ tile_off) {
+  __shared__ int cntw[RP_NW][RP_MAXB];          // pass 1: rows of (warp, bucket); pass 2: running write position
+  __shared__ int base_s[RP_MAXB + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NB = c.NB;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (long long t = blockIdx.x; t < c.ntiles; t += gridDim.x) {
+    const long long r0 = t * RP_TILE;
+    __syncthreads();
+    for (int i = tid; i < RP_NW * RP_MAXB; i += RP_THREADS) (&cntw[0][0])[i] = 0;
+    __syncthreads();
+    int bk[8], cl[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                 // warp w bins rows [w*256, w*256 + 256) of the tile, 8 groups of 32
+      const long long r = r0 + warp * 256 + u * 32 + lane;
+      const int ml = r < n ? __ldg(labels + r) : -1;
+      cl[u] = ml >> c.LCS;
+      bk[u] = ml < 0 ? -1 : ((ml & (c.CS - 1)) * RP_NW + (cl[u] & (RP_NW - 1)));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const unsigned same = __match_any_sync(0xffffffffu, bk[u]);
+      if (bk[u] >= 0 && (same & lt_mask) == 0) cntw[warp][bk[u]] += __popc(same);     // the group's first lane
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix: buckets in order, warps in order inside a bucket
+    if (tid < NB) {
+      int tot = 0;
+      for (int w = 0; w < RP_NW; ++w) tot += cntw[w][tid];
+      base_s[tid + 1] = tot;
+    }
+    if (tid == 0) base_s[0] = 0;
+    __syncthreads();
+    if (tid == 0) for (int b = 0; b < NB; ++b) base_s[b + 1] += base_s[b];
+    __syncthreads();
+    if (tid < NB) {
+      int pos = base_s[tid];
+      for (int w = 0; w < RP_NW; ++w) { const int cur = cntw[w][tid]; cntw[w][tid] = pos; pos += cur; }
+    }
+    for (int b = tid; b <= NB; b += RP_THREADS) tile_off[t * (RP_MAXB + 1) + b] = base_s[b];
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const unsigned same = __match_any_sync(0xffffffffu, bk[u]);
+      int pos = 0;
+      if (bk[u] >= 0) {
+        const int leader = __ffs(same) - 1;
+        if (lane == leader) { pos = cntw[warp][bk[u]]; cntw[warp][bk[u]] = pos + __popc(same); }
+        pos = __shfl_sync(same, pos, leader) + __popc(same & lt_mask);
+        bins[r0 + pos] = (unsigned)(warp * 256 + u * 32 + lane) | ((unsigned)cl[u] << 12);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Step 2: the M-step proper.  CTA (row block rb, cluster slice cs) owns the clusters c with c % CS == cs (KL of them:
+// their k/CS x d fp32 sums fit shared memory); warp w owns the local clusters (c / CS) % NW == w, i.e. bucket
+// cs * NW + w.  It walks its bucket's entries tile by tile (coalesced reads of the bin list) and GATHERS the rows,
+// whole rows, one coalesced load per warp and row, 16 loads in flight before the first one is consumed; rows are added
+// into the warp's clusters with plain read-add-write on shared memory (no atomics, row order: reproducible).
+// Every row of X is read exactly once over the CS CTAs of a row block; no label is scanned twice.
+// ------------------------------------------------------------------------------------------
+template <typename TX, int FPL>
 __global__ void __launch_bounds__(RP_THREADS, 1)
-rowpass_mstep_kernel(ChunkArgs a, RpCfg c) {
+rowpass_mstep_kernel(ChunkArgs a, RpCfg c, const unsigned* __restrict__ bins, const int* __restrict__ tile_off) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k = a.k, d = a.d, FS = c.FS;
-  const int rb = blockIdx.x / c.DS, ds = blockIdx.x % c.DS;
-  const int f0 = ds * FS;
-  float* sums_s = reinterpret_cast<float*>(smem + c.off_sums);       // [k][FS]
-  int* cnts_s = reinterpret_cast<int*>(smem + c.off_cnt);            // [k]
-  int* lab_s = reinterpret_cast<int*>(smem + c.off_lab);             // [2][RP_TR]
-  unsigned char* xs = smem + c.off_x;                                // [2][RP_TR][xrow_bytes]
+  const int k = a.k, d = a.d, CS = c.CS;
+  const int rb = blockIdx.x / CS, cs = blockIdx.x % CS;
+  constexpr int RW = 32 * FPL;                                       // floats per cluster row in shared memory
+  float* sums_s = reinterpret_cast<float*>(smem + c.off_sums);       // [KL][RW]
+  int* cnts_s = reinterpret_cast<int*>(smem + c.off_cnt);            // [KL]
   const TX* X = reinterpret_cast<const TX*>(a.X);
-  for (int i = tid; i < k * FS; i += RP_THREADS) sums_s[i] = 0.f;
-  for (int i = tid; i < k; i += RP_THREADS) cnts_s[i] = 0;
+  for (int i = tid; i < c.KL * RW; i += RP_THREADS) sums_s[i] = 0.f;
+  for (int i = tid; i < c.KL; i += RP_THREADS) cnts_s[i] = 0;
+  __syncthreads();
 
-  const long long ntiles = (a.n + RP_TR - 1) / RP_TR;
-  const int chunks = (int)(c.xrow_bytes / 16);                       // 16-byte chunks per row slice
-  const uint32_t xs_u = ptx::smem_u32(xs), lab_u = ptx::smem_u32(lab_s);
-  const uint32_t xbuf = (uint32_t)RP_TR * c.xrow_bytes;
-  // stage tile t (labels + this CTA's feature slice of its rows) into buffer b; rows past n are labelled -1.
-  // Chunks that start beyond the row pitch are skipped (their features are >= d and never read).
-  auto stage = [&](long long t, int b) {
-    const long long r0 = t * RP_TR;
-    const int rows = (int)min((long long)RP_TR, a.n - r0);
-    for (int e = tid; e < RP_TR * chunks; e += RP_THREADS) {
-      const int r = e / chunks, q = e - r * chunks;
-      const long long col = (long long)f0 + (long long)q * (16 / (int)sizeof(TX));
-      if (r < rows && col < a.ldx)
-        cp_async16(xs_u + (uint32_t)b * xbuf + (uint32_t)r * c.xrow_bytes + (uint32_t)q * 16u,
-                   X + (r0 + r) * a.ldx + col);
+  const long long t0 = (long long)rb * c.tiles_per_block;
+  const long long t1 = min(c.ntiles, t0 + c.tiles_per_block);
+  const int bucket = cs * RP_NW + warp;
+  const bool lane_on = lane * FPL < d;                               // this lane's piece holds real features
+  // Software pipeline: while the 16 rows of batch i are in flight, the entries of batch i + 1 (and the bucket bounds of
+  // the next tile) are already being fetched, so a batch costs ONE memory round trip.
+  long long t = t0;
+  int hi = 0, e0 = 0, nlo = 0, nhi = 0;
+  if (t0 < t1) {
+    e0 = __ldg(tile_off + t0 * (RP_MAXB + 1) + bucket);
+    hi = __ldg(tile_off + t0 * (RP_MAXB + 1) + bucket + 1);
+    if (t0 + 1 < t1) {
+      nlo = __ldg(tile_off + (t0 + 1) * (RP_MAXB + 1) + bucket);
+      nhi = __ldg(tile_off + (t0 + 1) * (RP_MAXB + 1) + bucket + 1);
     }
-    for (int r = tid; r < RP_TR; r += RP_THREADS) {
-      if (r < rows) cp_async4(lab_u + (uint32_t)(b * RP_TR + r) * 4u, a.labels + r0 + r);
-      else lab_s[b * RP_TR + r] = -1;
-    }
-    cp_async_commit();
-  };
-
-  long long t = rb;
-  int buf = 0;
-  if (t < ntiles) stage(t, 0);
-  __syncthreads();                                         // zeroed accumulators visible
-#pragma unroll 1
-  for (; t < ntiles; t += c.RB, buf ^= 1) {
-    const long long tn = t + c.RB;
-    if (tn < ntiles) { stage(tn, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
-    const int* lab = lab_s + buf * RP_TR;
-    const unsigned char* xb = xs + (size_t)buf * xbuf;
-    // warp w owns the clusters c with c % NW == w
-#pragma unroll 1
-    for (int base = 0; base < RP_TR; base += 32) {
-      const int ml = lab[base + lane];
-      unsigned m = __ballot_sync(0xffffffffu, ml >= 0 && (ml % RP_NW) == warp);
-#pragma unroll 1
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int cl = __shfl_sync(0xffffffffu, ml, b);
-        if (ds == 0 && lane == 0) cnts_s[cl] += 1;          // the warp owns cluster cl: no race
-        const TX* xr = reinterpret_cast<const TX*>(xb + (size_t)(base + b) * c.xrow_bytes);
-        float* sr = sums_s + (size_t)cl * FS;
-        for (int f = lane; f < FS; f += 32)
-          if (f0 + f < d) sr[f] += rp_to_float<TX>(xr[f]);
+  }
+  unsigned mine_n = 0u;
+  int nb_n = 0;
+  long long r0_n = 0;
+  auto advance = [&]() -> bool {            // warp-uniform: queue the next non-empty batch and issue its entry load
+    if (t >= t1) return false;
+    while (e0 >= hi) {
+      if (++t >= t1) return false;
+      e0 = nlo; hi = nhi;
+      if (t + 1 < t1) {
+        nlo = __ldg(tile_off + (t + 1) * (RP_MAXB + 1) + bucket);
+        nhi = __ldg(tile_off + (t + 1) * (RP_MAXB + 1) + bucket + 1);
       }
     }
-    __syncthreads();
+    nb_n = min(RP_BATCH, hi - e0);
+    r0_n = t * RP_TILE;
+    mine_n = lane < nb_n ? __ldg(bins + r0_n + e0 + lane) : 0u;
+    e0 += RP_BATCH;
+    return true;
+  };
+  bool have = advance();
+#pragma unroll 1
+  while (have) {
+    const unsigned mine = mine_n;
+    const int nb = nb_n;
+    const long long r0 = r0_n;
+    have = advance();
+    RowPiece<TX, FPL> x[RP_BATCH];
+    int cc[RP_BATCH];
+    const unsigned e_first = __shfl_sync(0xffffffffu, mine, 0);
+#pragma unroll
+    for (int q = 0; q < RP_BATCH; ++q) {
+      const unsigned e = __shfl_sync(0xffffffffu, mine, q);
+      cc[q] = (int)(e >> 12);
+      // rows past the batch re-load its first row (never used): the loads stay unconditional and back to back
+      const unsigned eq = q < nb ? e : e_first;
+      if (lane_on) x[q].load(X + (r0 + (long long)(eq & 0xfffu)) * a.ldx + lane * FPL);
+    }
+    __syncwarp();                                                    // all loads of the batch are issued before the first use
+#pragma unroll
+    for (int q = 0; q < RP_BATCH; ++q) {
+      if (q < nb) {
+        if (lane_on) x[q].add(sums_s + (size_t)cc[q] * RW + lane * FPL);
+        if (lane == 0) cnts_s[cc[q]] += 1;
+      }
+    }
   }
-  // ---- flush this CTA's [k][FS] block into slot rb of the partial sums ----
+  __syncthreads();
+  // ---- flush: local cluster cl is cluster cl * CS + cs ----
   float* g = reinterpret_cast<float*>(a.psum) + (size_t)rb * k * d;
-  for (int i = tid; i < k * FS; i += RP_THREADS) {
-    const int cl = i / FS, f = i - cl * FS;
-    if (f0 + f < d) g[(size_t)cl * d + f0 + f] = sums_s[i];
+  for (int i = tid; i < c.KL * RW; i += RP_THREADS) {
+    const int cl = i / RW, f = i - cl * RW;
+    const int cg = cl * CS + cs;
+    if (cg < k && f < d) g[(size_t)cg * d + f] = sums_s[i];
   }
-  if (ds == 0) {
-    int* gc = a.pcnt + (size_t)rb * k;
-    for (int i = tid; i < k; i += RP_THREADS) gc[i] = cnts_s[i];
+  int* gc = a.pcnt + (size_t)rb * k;
+  for (int i = tid; i < c.KL; i += RP_THREADS) {
+    const int cg = i * CS + cs;
+    if (cg < k) gc[cg] = cnts_s[i];
   }
 }
 
@@ -158,38 +267,51 @@ rowpass_dist_kernel(ChunkArgs a) {
   }
 }
 
-static bool make_rp_cfg(int k, int d, int esz, int sm_count, int psum_slots, long long n, RpCfg* c) {
+static bool make_rp_cfg(int k, int d, int sm_count, int psum_slots, long long n, RpCfg* c, int* fpl_out) {
   const Tc2Geom g = tc2_geom(k, d);
-  c->FS = g.FS; c->DS = g.DS;
-  int rb = sm_count / g.DS;
+  const int fpl = d <= 32 ? 1 : (d <= 64 ? 2 : 4);
+  *fpl_out = fpl;
+  c->CS = g.DS;                                       // cluster slices (geometry shared with the workspace sizing)
+  c->LCS = 0;
+  while ((1 << c->LCS) < c->CS) ++c->LCS;
+  c->NB = c->CS * RP_NW;
+  if (c->NB > RP_MAXB) return false;
+  c->KL = (k + c->CS - 1) / c->CS;
+  c->ntiles = (n + RP_TILE - 1) / RP_TILE;
+  int rb = sm_count / c->CS;
   if (rb < 1) rb = 1;
   if (rb > psum_slots) rb = psum_slots;
-  const long long ntiles = (n + RP_TR - 1) / RP_TR;
-  if (rb > ntiles) rb = (int)(ntiles > 0 ? ntiles : 1);
+  if (rb > c->ntiles) rb = (int)(c->ntiles > 0 ? c->ntiles : 1);
+  c->tiles_per_block = (c->ntiles + rb - 1) / rb;
+  rb = (int)((c->ntiles + c->tiles_per_block - 1) / c->tiles_per_block);     // no empty row blocks
   c->RB = rb;
-  c->xrow_bytes = (uint32_t)align_up((size_t)g.FS * esz, 16);
   uint32_t o = 0;
-  c->off_sums = o; o += (uint32_t)k * g.FS * 4;
-  c->off_cnt = o; o += (uint32_t)align_up((size_t)k * 4, 16);
-  c->off_lab = o; o += 2 * RP_TR * 4;
-  o = (uint32_t)align_up(o, 128);
-  c->off_x = o; o += 2u * RP_TR * c->xrow_bytes;
+  c->off_sums = o; o += (uint32_t)c->KL * 32u * fpl * 4u;
+  c->off_cnt = o; o += (uint32_t)align_up((size_t)c->KL * 4, 16);
   c->total = o;
   return o <= 227 * 1024;
 }
 
 int launch_rowpass_mstep(const ChunkArgs& a, int x_dtype, int sm_count, int* parts_out, cudaStream_t s) {
   if (!a.labels) return BKM_EINVAL;                     // the row pass is driven by the labels
+  if (x_dtype != BKM_BF16) return BKM_EDTYPE;
   RpCfg c;
-  const int esz = x_dtype == BKM_BF16 ? 2 : 4;
-  if (!make_rp_cfg(a.k, a.d, esz, sm_count, a.psum_slots, a.n, &c)) return BKM_EUNSUPPORTED;
-  if (x_dtype == BKM_BF16) {
-    BKM_CUDA_TRY(cudaFuncSetAttribute(rowpass_mstep_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.total));
-    rowpass_mstep_kernel<__nv_bfloat16><<<c.RB * c.DS, RP_THREADS, c.total, s>>>(a, c);
-  } else {
-    BKM_CUDA_TRY(cudaFuncSetAttribute(rowpass_mstep_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.total));
-    rowpass_mstep_kernel<float><<<c.RB * c.DS, RP_THREADS, c.total, s>>>(a, c);
+  int fpl = 0;
+  if (!make_rp_cfg(a.k, a.d, sm_count, a.psum_slots, a.n, &c, &fpl)) return BKM_EUNSUPPORTED;
+  unsigned* bins = reinterpret_cast<unsigned*>(a.bin_list);
+  int* tile_off = a.bin_off;
+  long long nbk = c.ntiles < (long long)sm_count * 4 ? c.ntiles : (long long)sm_count * 4;
+  rowpass_bin_kernel<<<(int)nbk, RP_THREADS, 0, s>>>(a.labels, a.n, c, bins, tile_off);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+#define RP_GO(F)                                                                                                   \
+  {                                                                                                                \
+    auto kern = rowpass_mstep_kernel<__nv_bfloat16, F>;                                                            \
+    BKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.total));           \
+    kern<<<c.RB * c.CS, RP_THREADS, c.total, s>>>(a, c, bins, tile_off);                                           \
   }
+  if (fpl == 1) RP_GO(1) else if (fpl == 2) RP_GO(2) else RP_GO(4)
+#undef RP_GO
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   *parts_out = c.RB;

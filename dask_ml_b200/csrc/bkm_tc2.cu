@@ -338,9 +338,12 @@ tc2_combine_kernel(ChunkArgs a, int S) {
 
 // ------------------------------------------------------------------------------------------
 // float64 re-check of the deferred rows (labels only: distances and sums of these shapes come from the row passes).
-// Thread j <-> centres j, j + 256, ...; float64 centres transposed [d][kp2] (coalesced); 8 rows per group.
+// Same form as the reference's float64 E-step (scikit-learn ArgKmin: ||c||^2 - 2 x.c, the row norm is common to all
+// centres): one DFMA per (row, centre, feature).  Thread j <-> centres j, j + 256, ...; float64 centres transposed
+// [d][kp2] (coalesced reads, L2-resident: every group of rows streams the whole [d][k] block from L2, so 16 rows share
+// one pass); the group's rows are staged as float64 in shared memory (broadcast reads).
 // ------------------------------------------------------------------------------------------
-static const int R2_ROWS = 8;
+static const int R2_ROWS = 16;
 
 template <typename TX>
 __device__ __forceinline__ float ld_as_float(const TX* p);
@@ -350,7 +353,7 @@ template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __
 template <typename TX>
 __global__ void __launch_bounds__(256)
 tc2_recheck_kernel(ChunkArgs a, int kp2) {
-  __shared__ float xs[R2_ROWS][128];
+  __shared__ double xs[128][R2_ROWS];            // [feature][row]: the rows of a feature are one 128-byte broadcast
   __shared__ double wd[R2_ROWS][8];
   __shared__ int wj[R2_ROWS][8];
   __shared__ long long rows_s[R2_ROWS];
@@ -365,6 +368,7 @@ tc2_recheck_kernel(ChunkArgs a, int kp2) {
   if ((int)blockIdx.x * R2_ROWS >= cnt) return;
   const int k = a.k, d = a.d, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double* gT = reinterpret_cast<const double*>(a.pack + a.L.off_c64T2);
+  const double* cn64 = reinterpret_cast<const double*>(a.pack + a.L.off_cn64);
   const TX* X = reinterpret_cast<const TX*>(a.X);
   for (int f0 = blockIdx.x * R2_ROWS; f0 < cnt; f0 += gridDim.x * R2_ROWS) {
     const int nr = min(R2_ROWS, cnt - f0);
@@ -373,7 +377,7 @@ tc2_recheck_kernel(ChunkArgs a, int kp2) {
     __syncthreads();
     for (int e = tid; e < R2_ROWS * 128; e += 256) {
       const int r = e >> 7, i = e & 127;
-      xs[r][i] = (r < nr && i < d) ? ld_as_float<TX>(X + rows_s[r] * a.ldx + i) : 0.f;
+      xs[i][r] = (r < nr && i < d) ? (double)ld_as_float<TX>(X + rows_s[r] * a.ldx + i) : 0.0;
     }
     __syncthreads();
     double bd[R2_ROWS];
@@ -384,14 +388,18 @@ tc2_recheck_kernel(ChunkArgs a, int kp2) {
       double s0[R2_ROWS];
 #pragma unroll
       for (int r = 0; r < R2_ROWS; ++r) s0[r] = 0.0;
+#pragma unroll 4
       for (int i = 0; i < d; ++i) {
         const double c0 = gT[(size_t)i * kp2 + j];
 #pragma unroll
-        for (int r = 0; r < R2_ROWS; ++r) { const double d0 = (double)xs[r][i] - c0; s0[r] = fma(d0, d0, s0[r]); }
+        for (int r = 0; r < R2_ROWS; ++r) s0[r] = fma(xs[i][r], c0, s0[r]);
       }
+      const double cn = cn64[j];
 #pragma unroll
-      for (int r = 0; r < R2_ROWS; ++r)
-        if (s0[r] < bd[r]) { bd[r] = s0[r]; bj[r] = j; }     // ascending j: the lowest index wins exact ties
+      for (int r = 0; r < R2_ROWS; ++r) {
+        const double dist = fma(-2.0, s0[r], cn);            // + ||x||^2 is common to all centres of the row
+        if (dist < bd[r]) { bd[r] = dist; bj[r] = j; }      // ascending j: the lowest index wins exact ties
+      }
     }
 #pragma unroll
     for (int r = 0; r < R2_ROWS; ++r) {
@@ -506,7 +514,7 @@ int launch_tc2(const ChunkArgs& a0, bool mstep, int sm_count, int* grid_out, cud
     BKM_CUDA_TRY(cudaGetLastError());
   }
   if (a.k > 1) {
-    tc2_recheck_kernel<__nv_bfloat16><<<sm_count * 2, 256, 0, s>>>(a, g.kp2);
+    tc2_recheck_kernel<__nv_bfloat16><<<sm_count * 4, 256, 0, s>>>(a, g.kp2);
     note_launch();
     BKM_CUDA_TRY(cudaGetLastError());
   }
