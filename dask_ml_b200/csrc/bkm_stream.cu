@@ -17,6 +17,7 @@
 #include "bkm_common.cuh"
 #include "bkm_ptx.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace bkm {
 
@@ -328,6 +329,371 @@ stream_chunk_kernel(ChunkArgs a, StreamSmem S) {
   }
 }
 
+// ==========================================================================================================
+// Two rows per thread (k <= 24): the FFMA2 pair is {row l, row l + 32} of a 64-row warp tile against ONE centre value
+// (broadcast operand), so every centre load (LDS.128 of four features) feeds two rows, the per-tile overheads (ring
+// refill, label masks, M-step loop) are paid once per 64 rows and the lane-owns-cluster M-step sees twice the rows per
+// cluster and pass (better lane utilisation: its trip count is the LARGEST list of the tile).  ncu of the one-row
+// kernel on C4 (profiles/r02_stream_kernel.md): 780 warp instructions and 235 shared-memory wavefronts per 32 rows, both
+// pipes near saturation; this layout needs ~430 / ~140.
+// ==========================================================================================================
+static const int S2_NSTG = 3;       // ring stages per warp (64 rows each)
+
+struct Stream2Smem {
+  uint32_t off_c, off_cn, off_sums, off_cnt, off_red, off_bar, off_slot, off_ring, stage_bytes, total;
+};
+static inline Stream2Smem stream2_smem(int k, int d, long long ldx, int kc, int dp) {
+  Stream2Smem S;
+  uint32_t o = 0;
+  S.off_c = o;    o += (uint32_t)kc * dp * 4;             // [kc][dp] floats: -2 c (zero padded)
+  S.off_cn = o;   o += (uint32_t)kc * 4;                  // [kc] ||c||^2 (+inf for j >= k)
+  o = (uint32_t)align_up(o, 16);
+  S.off_sums = o; o += (uint32_t)k * d * 4;
+  o = (uint32_t)align_up(o, 16);
+  S.off_cnt = o;  o += (uint32_t)k * 4;
+  o = (uint32_t)align_up(o, 16);
+  S.off_red = o;  o += SW * 8;
+  S.off_bar = o;  o += SW * S2_NSTG * 8;
+  S.off_slot = o; o += SW * 64 * 4;                       // per warp: two row masks per cluster
+  o = (uint32_t)align_up(o, 128);
+  S.stage_bytes = (uint32_t)(64 * ldx * 4);
+  S.off_ring = o; o += (uint32_t)SW * S2_NSTG * S.stage_bytes + 128;      // + slack: the M-step reads whole DP-float rows
+  S.total = o;
+  return S;
+}
+
+// DH = feature pairs (DP = 2 DH >= d), KC = centres rounded up to a multiple of 4 (<= 24)
+template <int DH, int KC, bool MSTEP>
+__global__ void __launch_bounds__(SW * 32, 2)
+stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
+  constexpr int DP = DH * 2;
+  constexpr int D4 = (DP + 3) / 4;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = a.d, k = a.k;
+  const int L = (int)a.ldx;
+  float* cs = reinterpret_cast<float*>(smem + S.off_c);
+  float* cns = reinterpret_cast<float*>(smem + S.off_cn);
+  float* sums_s = reinterpret_cast<float*>(smem + S.off_sums);
+  int* cnts_s = reinterpret_cast<int*>(smem + S.off_cnt);
+  double* red_s = reinterpret_cast<double*>(smem + S.off_red);
+  const float* gC = reinterpret_cast<const float*>(a.pack + a.L.off_cT);      // [k][d4] fp32, zero padded
+  const int d4 = a.L.d4;
+  const float* gCn = reinterpret_cast<const float*>(a.pack + a.L.off_cnT);
+  const double* gC64 = reinterpret_cast<const double*>(a.pack + a.L.off_c64);
+  const PackHeader* hdr = reinterpret_cast<const PackHeader*>(a.pack);
+  const float* X = reinterpret_cast<const float*>(a.X);
+
+  constexpr int CP = D4 * 4;                               // centre row pitch in shared memory (16-byte rows)
+  for (int i = tid; i < KC * CP; i += SW * 32) {
+    const int j = i / CP, f = i - j * CP;
+    cs[i] = (j < k && f < d) ? -2.f * gC[(size_t)j * d4 + f] : 0.f;
+  }
+  for (int j = tid; j < KC; j += SW * 32) cns[j] = j < k ? gCn[j] : CUDART_INF_F;
+  if (MSTEP) {
+    for (int i = tid; i < k * d; i += SW * 32) sums_s[i] = 0.f;
+    for (int i = tid; i < k; i += SW * 32) cnts_s[i] = 0;
+  }
+  const float cnmax = (float)hdr->cn_max;
+
+  unsigned char* ring = smem + S.off_ring + (size_t)warp * S2_NSTG * S.stage_bytes;
+  const uint32_t ring_u = smem_u32(ring);
+  const uint32_t bar0 = smem_u32(smem + S.off_bar) + (uint32_t)warp * S2_NSTG * 8u;
+  if (lane == 0) {
+    for (int s = 0; s < S2_NSTG; ++s) mbar_init(bar0 + 8u * s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long ntiles = (a.n + 63) >> 6;
+  const long long gw = (long long)blockIdx.x * SW + warp, nw = (long long)gridDim.x * SW;
+  const uint32_t stage_bytes = S.stage_bytes;
+  if (lane == 0) {
+#pragma unroll 1
+    for (int s = 0; s < S2_NSTG; ++s) {
+      const long long t = gw + (long long)s * nw;
+      if (t < ntiles - 1) {
+        mbar_expect_tx(bar0 + 8u * s, stage_bytes);
+        bulk_g2s(ring_u + (uint32_t)s * stage_bytes, X + t * 64 * (long long)L, stage_bytes, bar0 + 8u * s);
+      }
+    }
+  }
+
+  float macc[MSTEP ? DP : 1];
+#pragma unroll
+  for (int i = 0; i < (MSTEP ? DP : 1); ++i) macc[i] = 0.f;
+  int mcnt = 0;
+  double dsum = 0.0;
+  const bool want_dist = a.want_sum || a.min_out != nullptr;
+
+  long long it = 0;
+#pragma unroll 1
+  for (long long t = gw; t < ntiles; t += nw, ++it) {
+    const int s = (int)(it % S2_NSTG);
+    float* xs = reinterpret_cast<float*>(ring + (size_t)s * stage_bytes);
+    const long long r0 = t << 6;
+    const int rows = (int)min(64LL, a.n - r0);
+    if (t == ntiles - 1) {
+      const int nel = (rows - 1) * L + d;
+      const float* src = X + r0 * (long long)L;
+      for (int e = lane; e < nel; e += 32) xs[e] = src[e];
+      __syncwarp();
+    } else {
+      mbar_wait(bar0 + 8u * s, (uint32_t)((it / S2_NSTG) & 1));
+    }
+    const bool v0 = lane < rows, v1 = lane + 32 < rows;
+
+    // ---- two rows per thread, packed per feature: xp[i] = {x_i of row lane, x_i of row lane + 32} ----
+    unsigned long long xp[DP];
+    float xn0 = 0.f, xn1 = 0.f;
+    {
+      const float* xa = xs + lane * L;
+      const float* xb = xs + (lane + 32) * L;
+      if ((L & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < D4; ++q) {
+          float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+          if (v0 && q * 4 < d) va = *reinterpret_cast<const float4*>(xa + q * 4);
+          if (v1 && q * 4 < d) vb = *reinterpret_cast<const float4*>(xb + q * 4);
+          const float fa[4] = {va.x, va.y, va.z, va.w}, fb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (q * 4 + e < DP) {
+              const float ea = q * 4 + e < d ? fa[e] : 0.f, eb = q * 4 + e < d ? fb[e] : 0.f;
+              xp[q * 4 + e] = pack2(ea, eb);
+              xn0 = fmaf(ea, ea, xn0); xn1 = fmaf(eb, eb, xn1);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < DP; ++i) {
+          const float ea = (v0 && i < d) ? xa[i] : 0.f, eb = (v1 && i < d) ? xb[i] : 0.f;
+          xp[i] = pack2(ea, eb);
+          xn0 = fmaf(ea, ea, xn0); xn1 = fmaf(eb, eb, xn1);
+        }
+      }
+    }
+
+    // ---- E-step: dist pair {row0, row1} per centre ----
+    unsigned long long dp[KC];
+#pragma unroll
+    for (int g = 0; g < KC; g += 4) {
+      const float4 cnv = *reinterpret_cast<const float4*>(cns + g);
+      unsigned long long a0 = pack2(cnv.x, cnv.x), a1 = pack2(cnv.y, cnv.y), a2 = pack2(cnv.z, cnv.z), a3 = pack2(cnv.w, cnv.w);
+#pragma unroll
+      for (int q = 0; q < D4; ++q) {
+        const float4 c0 = *reinterpret_cast<const float4*>(cs + (g + 0) * CP + q * 4);
+        const float4 c1 = *reinterpret_cast<const float4*>(cs + (g + 1) * CP + q * 4);
+        const float4 c2 = *reinterpret_cast<const float4*>(cs + (g + 2) * CP + q * 4);
+        const float4 c3 = *reinterpret_cast<const float4*>(cs + (g + 3) * CP + q * 4);
+        const float f0[4] = {c0.x, c0.y, c0.z, c0.w}, f1[4] = {c1.x, c1.y, c1.z, c1.w};
+        const float f2[4] = {c2.x, c2.y, c2.z, c2.w}, f3[4] = {c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (q * 4 + e < DP) {
+            const unsigned long long xv = xp[q * 4 + e];
+            a0 = ffma2(xv, pack2(f0[e], f0[e]), a0); a1 = ffma2(xv, pack2(f1[e], f1[e]), a1);
+            a2 = ffma2(xv, pack2(f2[e], f2[e]), a2); a3 = ffma2(xv, pack2(f3[e], f3[e]), a3);
+          }
+      }
+      dp[g] = a0; dp[g + 1] = a1; dp[g + 2] = a2; dp[g + 3] = a3;
+    }
+    // ---- decode both rows: minimum, then FSET + FFMA per distance (see the one-row kernel) ----
+    int bjr[2];
+    double d2x[2] = {-1.0, -1.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float m1 = CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j + 1 < KC; j += 2) {
+        float lo0, hi0, lo1, hi1;
+        unpack2(dp[j], lo0, hi0); unpack2(dp[j + 1], lo1, hi1);
+        m1 = fmin3(m1, h ? hi0 : lo0, h ? hi1 : lo1);
+      }
+      const float xn = h ? xn1 : xn0;
+      const float thr = m1 + a.tau * (xn + cnmax);
+      float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+      for (int j = 0; j + 1 < KC; j += 2) {
+        float lo0, hi0, lo1, hi1;
+        unpack2(dp[j], lo0, hi0); unpack2(dp[j + 1], lo1, hi1);
+        h0 = fmaf(fset_le(h ? hi0 : lo0, thr), 1.f + (float)j * 0.0009765625f, h0);
+        h1 = fmaf(fset_le(h ? hi1 : lo1, thr), 1.f + (float)(j + 1) * 0.0009765625f, h1);
+      }
+      const float hits = h0 + h1;
+      int bj = (int)((hits - 1.f) * 1024.f + 0.5f);
+      const bool valid = h ? v1 : v0;
+      if (valid && !(hits >= 1.f && hits < 2.f) && k > 1) {
+        if (a.tau > 0.f) {
+          double bd = CUDART_INF;
+          bj = 0;
+          for (int j = 0; j < k; ++j) {
+            const double* c = gC64 + (size_t)j * d;
+            double sacc = 0.0;
+#pragma unroll
+            for (int i = 0; i < DP; ++i)
+              if (i < d) {
+                float ea, eb;
+                unpack2(xp[i], ea, eb);
+                const double df = (double)(h ? eb : ea) - c[i];
+                sacc = fma(df, df, sacc);
+              }
+            if (sacc < bd) { bd = sacc; bj = j; }
+          }
+          d2x[h] = bd;
+        } else {
+          bj = 0;
+          bool found = false;
+#pragma unroll
+          for (int j = 0; j < KC; ++j) {
+            float lo, hi;
+            unpack2(dp[j], lo, hi);
+            if (!found && (h ? hi : lo) == m1) { bj = j; found = true; }
+          }
+        }
+      }
+      if (k == 1) bj = 0;
+      if (!valid) bj = -1;
+      bjr[h] = bj;
+      if (valid) {
+        const long long row = r0 + lane + 32 * h;
+        if (a.labels) a.labels[row] = bj;
+        if (want_dist) {
+          double dd = d2x[h];
+          if (dd < 0.0) {
+            const float* cw = cs + (size_t)bj * CP;
+            float sacc = 0.f;
+#pragma unroll
+            for (int i = 0; i < DP; ++i)
+              if (i < d) {
+                float ea, eb;
+                unpack2(xp[i], ea, eb);
+                const float df = fmaf(0.5f, cw[i], h ? eb : ea);
+                sacc = fmaf(df, df, sacc);
+              }
+            dd = (double)sacc;
+          }
+          const double outv = a.squared ? dd : sqrt(dd);
+          dsum += outv;
+          if (a.min_out) reinterpret_cast<float*>(a.min_out)[row] = (float)outv;
+        }
+      }
+    }
+
+    // ---- M-step: lane j takes the rows of this 64-row tile labelled j ----
+    if (MSTEP) {
+      unsigned* slot = reinterpret_cast<unsigned*>(smem + S.off_slot) + warp * 64;
+      slot[lane] = 0u; slot[32 + lane] = 0u;
+      const unsigned same0 = __match_any_sync(0xffffffffu, bjr[0]);
+      const unsigned same1 = __match_any_sync(0xffffffffu, bjr[1]);
+      __syncwarp();
+      if (bjr[0] >= 0) slot[bjr[0]] = same0;
+      if (bjr[1] >= 0) slot[32 + bjr[1]] = same1;
+      __syncwarp();
+      unsigned mine0 = slot[lane], mine1 = slot[32 + lane];
+      mcnt += __popc(mine0) + __popc(mine1);
+#pragma unroll 1
+      while (__any_sync(0xffffffffu, (mine0 | mine1) != 0u)) {
+        if (mine0 | mine1) {
+          int b;
+          if (mine0) { b = __ffs(mine0) - 1; mine0 &= mine0 - 1; }
+          else { b = 32 + __ffs(mine1) - 1; mine1 &= mine1 - 1; }
+          const float* xr = xs + b * L;
+          if ((L & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < D4; ++q) {
+              const float4 v = *reinterpret_cast<const float4*>(xr + q * 4);
+              macc[q * 4 + 0] += v.x;
+              if (q * 4 + 1 < DP) macc[q * 4 + 1] += v.y;
+              if (q * 4 + 2 < DP) macc[q * 4 + 2] += v.z;
+              if (q * 4 + 3 < DP) macc[q * 4 + 3] += v.w;
+            }
+          } else {
+            // whole DP-float rows (the ring has slack behind it): entries >= d are never flushed
+#pragma unroll
+            for (int i = 0; i < (MSTEP ? DP : 1); ++i) macc[i] += xr[i];
+          }
+        }
+      }
+    }
+
+    // ---- refill this stage ----
+    __syncwarp();
+    if (lane == 0) {
+      const long long tn = t + (long long)S2_NSTG * nw;
+      if (tn < ntiles - 1) {
+        mbar_expect_tx(bar0 + 8u * s, stage_bytes);
+        bulk_g2s(ring_u + (uint32_t)s * stage_bytes, X + tn * 64 * (long long)L, stage_bytes, bar0 + 8u * s);
+      }
+    }
+  }
+
+  if (MSTEP) {
+    for (int w = 0; w < SW; ++w) {
+      if (warp == w && lane < k) {
+#pragma unroll
+        for (int i = 0; i < (MSTEP ? DP : 1); ++i)
+          if (i < d) sums_s[lane * d + i] += macc[i];
+        cnts_s[lane] += mcnt;
+      }
+      __syncthreads();
+    }
+    float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * k * d;
+    for (int i = tid; i < k * d; i += SW * 32) g[i] = sums_s[i];
+    int* gc = a.pcnt + (size_t)blockIdx.x * k;
+    for (int i = tid; i < k; i += SW * 32) gc[i] = cnts_s[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  if (lane == 0) red_s[warp] = dsum;
+  __syncthreads();
+  if (tid == 0) {
+    double sacc = 0.0;
+    for (int w = 0; w < SW; ++w) sacc += red_s[w];
+    a.pin[blockIdx.x] = sacc;
+  }
+}
+
+template <int DH, int KC>
+static int launch_stream2_dk(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
+  Stream2Smem S = stream2_smem(a.k, a.d, a.ldx, KC, (2 * DH + 3) / 4 * 4);
+  if (S.total > 227 * 1024) return BKM_EUNSUPPORTED;
+  const long long ntiles = (a.n + 63) / 64;
+  int occ = 0;
+#define STREAM2_GO(M)                                                                                       \
+  {                                                                                                         \
+    auto kern = stream2_chunk_kernel<DH, KC, M>;                                                            \
+    BKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));    \
+    BKM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SW * 32, S.total));              \
+    if (occ < 1) return BKM_EUNSUPPORTED;                                                                   \
+    long long grid = (long long)sm_count * occ;                                                             \
+    if (grid > a.psum_slots) grid = a.psum_slots;                                                           \
+    if (grid > a.part_slots) grid = a.part_slots;                                                           \
+    const long long need = (ntiles + SW - 1) / SW;                                                          \
+    if (grid > need) grid = need;                                                                           \
+    if (grid < 1) grid = 1;                                                                                 \
+    *grid_out = (int)grid;                                                                                  \
+    kern<<<(int)grid, SW * 32, S.total, s>>>(a, S);                                                         \
+  }
+  if (mstep) STREAM2_GO(true) else STREAM2_GO(false)
+#undef STREAM2_GO
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <int DH>
+static int launch_stream2_d(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
+  switch ((a.k + 3) / 4) {
+    case 1: return launch_stream2_dk<DH, 4>(a, mstep, sm_count, grid_out, s);
+    case 2: return launch_stream2_dk<DH, 8>(a, mstep, sm_count, grid_out, s);
+    case 3: return launch_stream2_dk<DH, 12>(a, mstep, sm_count, grid_out, s);
+    case 4: return launch_stream2_dk<DH, 16>(a, mstep, sm_count, grid_out, s);
+    case 5: return launch_stream2_dk<DH, 20>(a, mstep, sm_count, grid_out, s);
+    default: return launch_stream2_dk<DH, 24>(a, mstep, sm_count, grid_out, s);
+  }
+}
+
 bool stream_supported(int d, int k, int dtype) {
   return dtype == BKM_F32 && d >= 1 && d <= 16 && k >= 1 && k <= 32;
 }
@@ -378,6 +744,13 @@ static int launch_stream_d(const ChunkArgs& a, bool mstep, int sm_count, int* gr
 int launch_stream(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s) {
   if (!stream_supported(a.d, a.k, BKM_F32)) return BKM_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a.X) & 15) || a.ldx > 64) return BKM_EALIGN;
+  if (a.k <= 24 && a.ldx <= 32 && !getenv("BKM_STREAM_V1")) {        // two rows per thread
+    if (a.d <= 4) return launch_stream2_d<2>(a, mstep, sm_count, grid_out, s);
+    if (a.d <= 8) return launch_stream2_d<4>(a, mstep, sm_count, grid_out, s);
+    if (a.d <= 12) return launch_stream2_d<6>(a, mstep, sm_count, grid_out, s);
+    if (a.d <= 14) return launch_stream2_d<7>(a, mstep, sm_count, grid_out, s);
+    return launch_stream2_d<8>(a, mstep, sm_count, grid_out, s);
+  }
   // feature pairs (compile-time): d <= 4, 8, 12, 14, 16
   if (a.d <= 4) return launch_stream_d<2>(a, mstep, sm_count, grid_out, s);
   if (a.d <= 8) return launch_stream_d<4>(a, mstep, sm_count, grid_out, s);
