@@ -6,9 +6,10 @@
 
 Headline workload (BASELINE.json configs[1], "C2"): synthetic blobs 10M x 64 float32, k = 256, one chunk per GPU,
 fixed init = first k rows.  A *step* is one full Lloyd iteration as ``KMeans.fit`` runs it
-(``dask_ml_b200.cluster.k_means.lloyd_loop``): centre pack -> fused E+M kernel over the resident chunk -> (N>1: one
-all-reduce of [k*d sums | k counts | inertia]) -> centre update + shift -> ONE host read of the shift (the stop test,
-dask_ml/cluster/k_means.py:552-559).  With N>1 every rank holds its own 10M-row chunk (weak scaling).
+(``dask_ml_b200.cluster.k_means.lloyd_loop`` -> ``LloydState.run``): fused E+M kernel over the resident chunk -> (N>1:
+one all-reduce of [k*d sums | k counts | inertia]) -> ``bkm_finalize_step`` (centre update + shift + the stop test of
+dask_ml/cluster/k_means.py:552-559 ON THE DEVICE + the next iteration's centre pack); the host reads the loop state
+once per batch of 8 iterations.  With N>1 every rank holds its own 10M-row chunk (weak scaling).
 Rank 0 prints ONE JSON line.
 
 Numbers reported:
@@ -318,14 +319,13 @@ def time_lloyd(st, steps, warmup, barrier, world, dev):
     lloyd_loop(st, warmup, 0.0)
     barrier()
     kev = []
-    orig_step = st.step
 
-    def step_with_events():
+    def hook():
         pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         kev.append(pair)
-        orig_step(kernel_events=pair)
+        return pair
 
-    st.step = step_with_events
+    st.kernel_event_hook = hook
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -335,7 +335,7 @@ def time_lloyd(st, steps, warmup, barrier, world, dev):
     ev1.record()
     barrier()
     launches = st.be.launch_count() - l0
-    st.step = orig_step
+    st.kernel_event_hook = None
     ms_total = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
@@ -580,7 +580,7 @@ def main():
         "config": cfg,
         "detail": {"arithmetic": "split-fp16 (hi,lo) x3 product on tcgen05 kind::f16, fp32 accumulate, float64 re-check of near-ties + float64 centre update",
                    "l2": "inputs (%.2f GB per GPU) are larger than L2 (126 MB); no explicit flush" % (n * N_FEAT * 4 / 1e9),
-                   "step": "lloyd_loop(): pack + fused E+M kernel + re-check + reduce (+ all-reduce) + finalize + ONE host read of the shift per iteration, as KMeans.fit runs it",
+                   "step": "lloyd_loop() as KMeans.fit runs it: fused E+M kernel + reduce + re-check (+ all-reduce) + finalize_step (centre update, shift, device-side stop test, next pack); one host read of the loop state per 8 iterations",
                    "kernel_family": fam_c2, "final_shift": shift},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": par,
         "allreduce_us": allreduce_us, "configs": configs, "cpu_baseline": cpu,

@@ -17,6 +17,8 @@ BKM_BF16 = 2
 FLAG_FORCE_SIMT = 1
 FLAG_FORCE_TC = 2
 FLAG_NO_RECHECK = 4
+FLAG_FIRST_CHUNK = 8
+FLAG_COUNTS_F64 = 16
 
 _c_void_p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -35,7 +37,11 @@ SIGNATURES = {
     "bkm_pack_centers": (_int, [_c_void_p, _int, _int, _int, _c_void_p, ctypes.c_size_t, _c_void_p]),
     "bkm_workspace_bytes": (_int, [_i64, _int, _int, _int, _szp]),
     "bkm_lloyd_chunk": (_int, [_c_void_p, _i64, _int, _i64, _int, _c_void_p, _int, _c_void_p, _c_void_p,
-                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, ctypes.c_size_t, _int, _c_void_p]),
+                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, ctypes.c_size_t, _int, _c_void_p, _c_void_p]),
+    "bkm_loop_state_bytes": (_int, [_szp]),
+    "bkm_loop_reset": (_int, [_c_void_p, _dbl, _c_void_p, _int, _c_void_p]),
+    "bkm_finalize_step": (_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _int, _int, _int, _c_void_p,
+                                 ctypes.c_size_t, _c_void_p]),
     "bkm_assign_chunk": (_int, [_c_void_p, _i64, _int, _i64, _int, _c_void_p, _int, _c_void_p, _c_void_p,
                                 _int, _c_void_p, _c_void_p, ctypes.c_size_t, _int, _c_void_p]),
     "bkm_sample_chunk": (_int, [_c_void_p, _i64, _int, _dbl, _u64, _u64, _c_void_p, _i64, _c_void_p, _c_void_p]),

@@ -450,18 +450,28 @@ def evaluate_cost(X, centers):
 # EM steps
 # ---------------------------------------------------------------------------------------
 class LloydState(object):
-    """Device-resident state of the Lloyd loop; ``step()`` is one full iteration:
-    fused E+M kernel per chunk -> one all-reduce -> centre update + shift (k_means.py:522-555).
-    No host synchronisation happens inside ``step()``."""
+    """Device-resident state of the Lloyd loop (k_means.py:522-560).
+
+    Two ways to drive it:
+      * ``run(max_iter, tol)`` — the DEVICE-RESIDENT loop (CUDA backend): per iteration one fused E+M call per chunk
+        (the first one overwrites the accumulators, no memsets), one all-reduce of ``[k*d sums | k counts | inertia]``
+        when distributed, and ``bkm_finalize_step`` (centre update + shift + stop test + the next iteration's centre
+        pack in one kernel).  The stop test runs on the device; the host enqueues ``sync_every`` iterations at a time
+        and reads the 40-byte loop state once per batch; iterations enqueued after convergence are no-ops.
+      * ``step()`` / ``accept()`` — one iteration with the shift left on the device (the CPU checker backend of the
+        tests and ``lloyd_iteration_host`` use the same arithmetic through ``finalize``).
+    """
 
     def __init__(self, X, centers):
         be = X.backend
         self.X, self.be = X, be
         k, d = centers.shape
         self.k, self.d = int(k), int(d)
-        # private copy: the state is updated in place and must never alias the caller's `init`
-        self.C = torch.from_numpy(np.array(centers, dtype=np.float64, order="C", copy=True)).to(be.device)
-        self.C_new = be.empty((k, d), torch.float64)
+        # private copies: the state is updated in place and must never alias the caller's `init`.
+        # Two centre buffers: iteration i reads Cb[cur] and writes Cb[cur ^ 1].
+        c0 = torch.from_numpy(np.array(centers, dtype=np.float64, order="C", copy=True)).to(be.device)
+        self.Cb = [c0, be.empty((k, d), torch.float64)]
+        self.cur = 0
         # one buffer so that the per-iteration collective is a single all-reduce
         self.red = be.zeros((k * d + k + 1,), torch.float64)
         self.sums = self.red[: k * d]
@@ -471,6 +481,18 @@ class LloydState(object):
         self.shift = be.zeros((1,), torch.float64)
         self.labels = [be.empty((int(x.shape[0]),), torch.int32) for x in X.chunks]
         self.pack = None
+        self.device_loop = hasattr(be, "finalize_step")
+        self.kernel_event_hook = None        # bench.py: () -> (start_event, end_event) around the chunk kernels
+        self.sync_every = 8
+
+    # the current centres / the other buffer
+    @property
+    def C(self):
+        return self.Cb[self.cur]
+
+    @property
+    def C_new(self):
+        return self.Cb[self.cur ^ 1]
 
     def step(self, kernel_events=None):
         be, X, k = self.be, self.X, self.k
@@ -491,7 +513,47 @@ class LloydState(object):
         be.finalize(self.sums, self.counts, self.C, self.C_new, self.shift)
 
     def accept(self):
-        self.C, self.C_new = self.C_new, self.C
+        self.cur ^= 1
+
+    def run(self, max_iter, tol):
+        """The device-resident loop.  Returns ``(shift, index of the last iteration, accepted)`` like ``lloyd_loop``."""
+        be, X, k = self.be, self.X, self.k
+        state, hist = be.loop_state_new(tol, max_iter)
+        self.pack = be.pack_centers(self.C, X.dtype, out=self.pack)       # iteration 0's pack; later ones come from finalize_step
+        work = [(x, lab) for x, lab in zip(X.chunks, self.labels) if int(x.shape[0]) > 0]
+        base = self.cur
+        issued = 0
+        done = n_iter = 0
+        shift = None
+        logged = 0
+        while issued < max_iter and not done:
+            for _ in range(min(self.sync_every, max_iter - issued)):
+                c_in, c_out = self.Cb[(base + issued) & 1], self.Cb[(base + issued + 1) & 1]
+                ev = self.kernel_event_hook() if self.kernel_event_hook is not None else None
+                if ev is not None:
+                    ev[0].record()
+                if not work:
+                    self.red.zero_()                  # a rank without rows still takes part in the all-reduce
+                for j, (x, lab) in enumerate(work):
+                    be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts_f, None, first=(j == 0),
+                                   loop_state=state)
+                if ev is not None:
+                    ev[1].record()
+                X.comm.allreduce_sum_(self.red)
+                be.finalize_step(self.red, c_in, c_out, state, self.pack, X.dtype)
+                issued += 1
+            done, n_iter, shift = be.loop_state_read(state)      # the only host synchronisation of the batch
+            _check_engine(be, shift, "the centre shift")
+            if logger.isEnabledFor(logging.INFO):
+                for v in hist[logged:n_iter].cpu().numpy().tolist():
+                    logger.info("Lloyd loop %2d. Shift: %0.4f", logged, v)
+                    logged += 1
+        if shift is None:
+            return None, -1, False
+        # converged in iteration n_iter - 1: its update was NOT taken over (Q3) -> the centres it read are current
+        self.cur = (base + n_iter - 1) & 1 if done else (base + n_iter) & 1
+        self.shift.fill_(shift)
+        return shift, n_iter - 1, not done
 
     def relabel(self, squared):
         """E-step only against the current centres; returns the summed min distance tensor."""
@@ -518,10 +580,14 @@ def _check_engine(be, value, what):
 
 
 def lloyd_loop(st, max_iter, tol):
-    """The Lloyd iterations of k_means.py:522-560 over a ``LloydState``: one ``step()`` (fused E+M kernels, all-reduce,
-    centre update) and ONE host synchronisation (the shift, k_means.py:552) per iteration.  ``bench.py`` times this very
-    function.  Returns ``(shift, index of the last iteration, accepted)``; ``accepted`` tells whether ``st.C`` already
-    holds the centres computed by the last iteration (False after the convergence ``break``, Q3)."""
+    """The Lloyd iterations of k_means.py:522-560 over a ``LloydState``.  ``bench.py`` times this very function.
+    CUDA backend: ``LloydState.run`` (device-resident stop test, one host read of the loop state per batch of
+    iterations).  Checker backend of the CPU tests: one ``step()`` and one host read of the shift per iteration.
+    Returns ``(shift, index of the last iteration, accepted)``; ``accepted`` tells whether ``st.C`` already holds the
+    centres computed by the last iteration (False after the convergence ``break``, Q3)."""
+    if getattr(st, "device_loop", False):
+        with _timer("Lloyd loop (device-resident, %d iterations at most)" % max_iter, _logger=logger):
+            return st.run(max_iter, tol)
     shift = None
     i = -1
     accepted = False

@@ -8,6 +8,9 @@ unsigned int tc_abort_code();
 void tc_abort_detail(unsigned int* out64);
 void tc_abort_reset();
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s);
+int launch_loop_reset(void* state, double tol, double* hist, int hist_cap, cudaStream_t s);
+int launch_finalize_step(const double* red, const double* c_in, double* c_out, void* state, int k, int d, int dtype,
+                         void* pack, cudaStream_t s);
 int launch_finalize(const double* sums, const long long* counts, const double* Cold, double* Cnew,
                     double* shift, int k, int d, cudaStream_t s);
 int launch_sample(const void* d2, long long n, int dtype, double eop, uint64_t seed, uint64_t off,
@@ -59,7 +62,7 @@ static float tau_for(int d, int dtype, int flags, int family) {
 static int chunk_common(const void* X, long long n, int d, long long ldx, int x_dtype,
                         const void* pack, int k, int* labels, void* min_out, int squared,
                         bool mstep, double* sums, long long* counts, double* dist_sum,
-                        void* ws, size_t ws_bytes, int flags, cudaStream_t s) {
+                        void* ws, size_t ws_bytes, int flags, const void* loop_state, cudaStream_t s) {
   if (n < 0 || d <= 0 || k <= 0 || ldx < d) return BKM_EINVAL;
   if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
   if (!pack || !ws) return BKM_EINVAL;
@@ -87,6 +90,9 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   a.defer_cnt = (int*)((unsigned char*)ws + W.off_flag);
   a.defer_idx = (int*)((unsigned char*)ws + W.off_defer);
   a.out_sums = sums; a.out_counts = counts; a.out_dist_sum = dist_sum;
+  a.skip = loop_state ? &reinterpret_cast<const LoopState*>(loop_state)->done : nullptr;
+  a.first_chunk = (flags & BKM_FLAG_FIRST_CHUNK) ? 1 : 0;
+  a.counts_f64 = (flags & BKM_FLAG_COUNTS_F64) ? 1 : 0;
   a.rec = reinterpret_cast<float4*>((unsigned char*)ws + W.off_rec);
   a.bin_list = (unsigned char*)ws + W.off_bin;
   a.bin_off = (int*)((unsigned char*)ws + W.off_binoff);
@@ -123,7 +129,10 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (rc) return rc;
   // grid < 0: the generic kernel ran in GLOBAL mode (sums accumulated by atomics into slot 0)
   const int g = grid < 0 ? -grid : grid;
-  return launch_reduce_partials(a, grid < 0 ? 1 : g, g, g, mstep, x_dtype, sums, counts, dist_sum, s);
+  rc = launch_reduce_partials(a, grid < 0 ? 1 : g, g, g, mstep, x_dtype, sums, counts, dist_sum, s);
+  if (rc) return rc;
+  if (family == 1) rc = launch_tc_recheck(a, mstep, sm, s);     // float64 decisions of the deferred rows, added on top
+  return rc;
 }
 
 }  // namespace bkm
@@ -200,9 +209,9 @@ int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out) {
 int bkm_lloyd_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, const void* pack,
                     int k, int32_t* labels, void* min_d2, double* sums, int64_t* counts,
                     double* inertia, void* workspace, size_t workspace_bytes, int flags,
-                    void* stream) {
+                    const void* loop_state, void* stream) {
   return chunk_common(X, n, d, ldx, x_dtype, pack, k, labels, min_d2, 1, true, sums,
-                      (long long*)counts, inertia, workspace, workspace_bytes, flags,
+                      (long long*)counts, inertia, workspace, workspace_bytes, flags, loop_state,
                       (cudaStream_t)stream);
 }
 
@@ -210,7 +219,7 @@ int bkm_assign_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, 
                      int k, int32_t* labels, void* min_dist, int squared, double* dist_sum,
                      void* workspace, size_t workspace_bytes, int flags, void* stream) {
   return chunk_common(X, n, d, ldx, x_dtype, pack, k, labels, min_dist, squared ? 1 : 0, false,
-                      nullptr, nullptr, dist_sum, workspace, workspace_bytes, flags,
+                      nullptr, nullptr, dist_sum, workspace, workspace_bytes, flags, nullptr,
                       (cudaStream_t)stream);
 }
 
@@ -241,6 +250,28 @@ int bkm_finalize(const double* sums, const int64_t* counts, const double* center
   if (!sums || !counts || !centers_old || !centers_new || !shift || k <= 0 || d <= 0) return BKM_EINVAL;
   return launch_finalize(sums, (const long long*)counts, centers_old, centers_new, shift, k, d,
                          (cudaStream_t)stream);
+}
+
+int bkm_loop_state_bytes(size_t* out) {
+  if (!out) return BKM_EINVAL;
+  *out = sizeof(LoopState);
+  return 0;
+}
+
+int bkm_loop_reset(void* loop_state, double tol, double* shift_hist, int hist_cap, void* stream) {
+  if (!loop_state || hist_cap < 0 || (hist_cap > 0 && !shift_hist)) return BKM_EINVAL;
+  if ((uintptr_t)loop_state & 7) return BKM_EALIGN;
+  return launch_loop_reset(loop_state, tol, shift_hist, hist_cap, (cudaStream_t)stream);
+}
+
+int bkm_finalize_step(const double* reduced, const double* centers_in, double* centers_out, void* loop_state,
+                      int k, int d, int x_dtype, void* pack, size_t pack_bytes, void* stream) {
+  if (!reduced || !centers_in || !centers_out || !loop_state || !pack || k <= 0 || d <= 0) return BKM_EINVAL;
+  if (centers_in == centers_out) return BKM_EINVAL;
+  if (!dtype_ok(x_dtype)) return BKM_EDTYPE;
+  if (pack_bytes < pack_layout(k, d, x_dtype).total) return BKM_EWORKSPACE;
+  if (((uintptr_t)pack & 255) || ((uintptr_t)loop_state & 7)) return BKM_EALIGN;
+  return launch_finalize_step(reduced, centers_in, centers_out, loop_state, k, d, x_dtype, pack, (cudaStream_t)stream);
 }
 
 int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, int* flag,

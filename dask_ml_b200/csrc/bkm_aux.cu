@@ -142,15 +142,16 @@ __global__ void pack_header_kernel(unsigned char* pack, PackLayout L) {
 // Small (k, d) — every shape the tensor path takes — are packed by ONE kernel: each CTA recomputes the two
 // global quantities (max |c| -> scale, all ||c||^2 -> cn_max; k*d is a few thousand elements) and then writes
 // its share of every layout.  Four dependent launches cost more than the work itself.
-__global__ void __launch_bounds__(1024)
-pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L) {
-  extern __shared__ double cn_s[];        // [k]
+// The body is shared by pack_fused_kernel (centres read from memory) and finalize_step_fused_kernel (centres computed
+// on the fly from the reduced sums and counts): `C(i)` yields element i of the row-major (k, d) float64 centres.
+template <typename Src>
+__device__ __forceinline__ void pack_fused_body(Src C, unsigned char* pack, const PackLayout& L, double* cn_s) {
   __shared__ double red[32];
   const int k = L.k, d = L.d, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // ---- max |c| -> scale
   double m = 0.0;
 #pragma unroll 8
-  for (int i = tid; i < k * d; i += 1024) m = fmax(m, fabs(C[i]));
+  for (int i = tid; i < k * d; i += 1024) m = fmax(m, fabs(C(i)));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) red[wid] = m;
@@ -165,7 +166,7 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
   // ---- ||c_j||^2 (one warp per centre, same summation order as pack_norms_kernel) and their maximum
   for (int j = wid; j < k; j += 32) {
     double s = 0.0;
-    for (int i = lane; i < d; i += 32) { double v = C[(size_t)j * d + i]; s = fma(v, v, s); }
+    for (int i = lane; i < d; i += 32) { double v = C((size_t)j * d + i); s = fma(v, v, s); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) cn_s[j] = s;
@@ -186,13 +187,13 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
   // ---- this CTA's share of the layouts
   const int gt = blockIdx.x * 1024 + tid, nth = gridDim.x * 1024;
   double* c64 = reinterpret_cast<double*>(pack + L.off_c64);
-  for (int i = gt; i < k * d; i += nth) c64[i] = C[i];
+  for (int i = gt; i < k * d; i += nth) c64[i] = C(i);
   double* cn64 = reinterpret_cast<double*>(pack + L.off_cn64);
   if (L.dtype != BKM_F64) {
     float* cT = reinterpret_cast<float*>(pack + L.off_cT);
     for (int i = gt; i < k * L.d4; i += nth) {
       int r = i / L.d4, c = i - r * L.d4;
-      cT[i] = c < d ? (float)C[(size_t)r * d + c] : 0.f;
+      cT[i] = c < d ? (float)C((size_t)r * d + c) : 0.f;
     }
     if (d <= L.dh) {
       __half* bhi = reinterpret_cast<__half*>(pack + L.off_bhi);
@@ -201,7 +202,7 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
         int r = i / L.dh, c = i - r * L.dh;
         __half hi = __float2half_rn(0.f), lo = hi;
         if (r < k && c < d) {
-          const double v = -2.0 * sc * C[(size_t)r * d + c];
+          const double v = -2.0 * sc * C((size_t)r * d + c);
           hi = __double2half(v);
           lo = __double2half(v - (double)__half2float(hi));
         }
@@ -212,7 +213,7 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
       double* cTT = reinterpret_cast<double*>(pack + L.off_c64T);
       for (int i = gt; i < d * L.kp; i += nth) {
         int f = i / L.kp, j = i - f * L.kp;
-        cTT[i] = j < k ? C[(size_t)j * d + f] : 0.0;
+        cTT[i] = j < k ? C((size_t)j * d + f) : 0.0;
       }
     }
     float* cn32 = reinterpret_cast<float*>(pack + L.off_cn32);
@@ -236,10 +237,119 @@ pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout 
     double* cT = reinterpret_cast<double*>(pack + L.off_cT);
     for (int i = gt; i < k * L.d4; i += nth) {
       int r = i / L.d4, c = i - r * L.d4;
-      cT[i] = c < d ? C[(size_t)r * d + c] : 0.0;
+      cT[i] = c < d ? C((size_t)r * d + c) : 0.0;
     }
     for (int j = gt; j < k; j += nth) { cn64[j] = cn_s[j]; reinterpret_cast<double*>(pack + L.off_cnT)[j] = cn_s[j]; }
   }
+}
+
+struct CentreFromMemory {
+  const double* p;
+  __device__ __forceinline__ double operator()(size_t i) const { return p[i]; }
+};
+
+__global__ void __launch_bounds__(1024)
+pack_fused_kernel(const double* __restrict__ C, unsigned char* pack, PackLayout L) {
+  extern __shared__ double cn_s[];        // [k]
+  pack_fused_body(CentreFromMemory{C}, pack, L, cn_s);
+}
+
+// ---------------------------------------------------------------------------------------
+// One Lloyd iteration's tail in ONE kernel (small k*d, i.e. every shape of the fused chunk kernels):
+//   C' = sums / max(counts, 1)  (k_means.py:548-551, empty cluster -> zero vector)
+//   shift = ||C - C'||_F^2      (k_means.py:555)        -> LoopState.shift, hist[n_iter], n_iter += 1
+//   if shift < tol: LoopState.done = 1, C' is NOT taken over (k_means.py:558-560: break before the assignment)
+//   else: c_out = C', and the centre pack for the NEXT iteration is built from C' right here.
+// Every CTA recomputes the shift (fixed order -> the same value and the same decision everywhere) and the two global
+// quantities of the pack; centres are read from c_in and written to c_out (two buffers: no CTA reads what another one
+// writes).  red = [k*d sums | k counts as float64 | inertia] is the all-reduced buffer of the step.
+// ---------------------------------------------------------------------------------------
+struct CentreFromSums {
+  const double* red;
+  int kd, d;
+  __device__ __forceinline__ double operator()(size_t i) const {
+    const double c = red[kd + (int)(i / (size_t)d)];
+    return red[i] / (c > 1.0 ? c : 1.0);
+  }
+};
+
+__global__ void __launch_bounds__(1024)
+finalize_step_fused_kernel(const double* __restrict__ red, const double* __restrict__ c_in, double* __restrict__ c_out,
+                           LoopState* st, unsigned char* pack, PackLayout L) {
+  extern __shared__ double cn_s[];        // [k]
+  __shared__ double sred[32];
+  if (st->done) return;
+  const int k = L.k, d = L.d, kd = k * d, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const CentreFromSums cnew{red, kd, d};
+  double acc = 0.0;
+  for (int i = tid; i < kd; i += 1024) { const double df = c_in[i] - cnew(i); acc = fma(df, df, acc); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) sred[wid] = acc;
+  __syncthreads();
+  double shift = 0.0;
+  for (int w = 0; w < 32; ++w) shift += sred[w];
+  __syncthreads();
+  const bool converged = shift < st->tol;
+  if (!converged) {
+    for (int i = blockIdx.x * 1024 + tid; i < kd; i += gridDim.x * 1024) c_out[i] = cnew(i);
+    pack_fused_body(cnew, pack, L, cn_s);
+  }
+  // the state is written last, by one thread of the last CTA to get here (every CTA has read st->done / st->tol)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(reinterpret_cast<unsigned int*>(&st->pad), 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && tid == 0) {
+    st->pad = 0;
+    st->shift = shift;
+    if (st->hist && st->n_iter < st->hist_cap) st->hist[st->n_iter] = shift;
+    st->n_iter += 1;
+    __threadfence();
+    if (converged) st->done = 1;
+  }
+}
+
+// Large k*d: single-CTA state update (shift, stop test, centre hand-over); the pack follows as separate kernels.
+__global__ void __launch_bounds__(1024)
+finalize_state_kernel(const double* __restrict__ red, const double* __restrict__ c_in, double* __restrict__ c_out,
+                      LoopState* st, int k, int d) {
+  __shared__ double sred[32];
+  if (st->done) return;
+  const int kd = k * d, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const CentreFromSums cnew{red, kd, d};
+  double acc = 0.0;
+  for (int i = tid; i < kd; i += 1024) { const double df = c_in[i] - cnew(i); acc = fma(df, df, acc); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) sred[wid] = acc;
+  __syncthreads();
+  double shift = 0.0;
+  for (int w = 0; w < 32; ++w) shift += sred[w];
+  const bool converged = shift < st->tol;
+  // on convergence c_out = c_in, so that the pack kernels that follow (and the host) always read c_out
+  for (int i = tid; i < kd; i += 1024) c_out[i] = converged ? c_in[i] : cnew(i);
+  __syncthreads();
+  if (tid == 0) {
+    st->shift = shift;
+    if (st->hist && st->n_iter < st->hist_cap) st->hist[st->n_iter] = shift;
+    st->n_iter += 1;
+    __threadfence();
+    if (converged) st->done = 2;       // 2: converged in THIS iteration (bkm_finalize_step's pack still runs once)
+  }
+}
+
+__global__ void loop_reset_kernel(LoopState* st, double tol, double* hist, int hist_cap) {
+  st->done = 0; st->n_iter = 0; st->hist_cap = hist_cap; st->pad = 0;
+  st->tol = tol; st->shift = CUDART_INF; st->hist = hist;
+}
+
+int launch_loop_reset(void* state, double tol, double* hist, int hist_cap, cudaStream_t s) {
+  loop_reset_kernel<<<1, 1, 0, s>>>(reinterpret_cast<LoopState*>(state), tol, hist, hist_cap);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 // Layouts of the large-shape tensor path (bkm_tc2.cu), written after the float64 norms:
@@ -312,6 +422,23 @@ int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream
   return launch_pack_tc2(C, L, pack, s);
 }
 
+int launch_finalize_step(const double* red, const double* c_in, double* c_out, void* state, int k, int d, int dtype,
+                         void* pack, cudaStream_t s) {
+  PackLayout L = pack_layout(k, d, dtype);
+  LoopState* st = reinterpret_cast<LoopState*>(state);
+  if (k <= 2048 && (long long)k * d <= 65536 && !tc2_shape(d, k, dtype)) {
+    int nb = (L.kp * L.dk + 2047) / 2048; if (nb > 16) nb = 16; if (nb < 1) nb = 1;
+    finalize_step_fused_kernel<<<nb, 1024, (size_t)k * 8, s>>>(red, c_in, c_out, st, (unsigned char*)pack, L);
+    note_launch();
+    BKM_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  finalize_state_kernel<<<1, 1024, 0, s>>>(red, c_in, c_out, st, k, d);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return launch_pack(c_out, k, d, dtype, pack, s);
+}
+
 // ---------------------------------------------------------------------------------------
 // reduce_partials: fold the per-CTA partials of one chunk into the float64 accumulators in a
 // FIXED order (CTA 0,1,2,...), so a chunk's contribution is bit-reproducible run to run.
@@ -320,7 +447,9 @@ template <typename PS>
 __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* __restrict__ pcnt,
                                        const double* __restrict__ pin, int cnt_parts, int pin_parts, int sum_parts,
                                        int kd, int k, bool mstep,
-                                       double* sums, long long* counts, double* dist_sum) {
+                                       double* sums, long long* counts, double* dist_sum,
+                                       const int* skip, int first, int counts_f64) {
+  if (skip && *skip) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
   // The additions run in CTA order (that is what makes a chunk's contribution reproducible); the loads of a
@@ -337,7 +466,7 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
         for (int q = 0; q < 16; ++q) s += (double)v[q];
       }
       for (; g < sum_parts; ++g) s += (double)psum[(size_t)g * kd + i];
-      sums[i] += s;
+      sums[i] = first ? s : sums[i] + s;
     }
     // counts: the last CTAs take them (the first ones already carry the tail of the sums loop)
     for (int i = nth - 1 - tid; i < k; i += nth) {
@@ -351,7 +480,8 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
         for (int q = 0; q < 16; ++q) c += v[q];
       }
       for (; g < cnt_parts; ++g) c += pcnt[(size_t)g * k + i];
-      counts[i] += c;
+      if (counts_f64) { double* cf = reinterpret_cast<double*>(counts); cf[i] = first ? (double)c : cf[i] + (double)c; }
+      else counts[i] = first ? c : counts[i] + c;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32 && dist_sum) {
@@ -360,7 +490,7 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
     for (int g = threadIdx.x; g < pin_parts; g += 32) s += pin[g];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) *dist_sum += s;
+    if (threadIdx.x == 0) *dist_sum = first ? s : *dist_sum + s;
   }
 }
 
@@ -373,10 +503,10 @@ int launch_reduce_partials(const ChunkArgs& a, int sum_parts, int cnt_parts, int
   int nb = (kd + 255) / 256; if (nb > 148) nb = 148; if (nb < 1) nb = 1;
   if (dtype != BKM_F64)
     reduce_partials_kernel<float><<<nb, 256, 0, s>>>((const float*)a.psum, a.pcnt, a.pin, cnt_parts, pin_parts, sum_parts,
-                                                     kd, a.k, mstep, sums, counts, dist_sum);
+                                                     kd, a.k, mstep, sums, counts, dist_sum, a.skip, a.first_chunk, a.counts_f64);
   else
     reduce_partials_kernel<double><<<nb, 256, 0, s>>>((const double*)a.psum, a.pcnt, a.pin, cnt_parts, pin_parts, sum_parts,
-                                                      kd, a.k, mstep, sums, counts, dist_sum);
+                                                      kd, a.k, mstep, sums, counts, dist_sum, a.skip, a.first_chunk, a.counts_f64);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -182,9 +182,24 @@ struct ChunkArgs {
   float4* rec;        // large-shape tensor path: [S][n] partial arg-min records {m1, m2, label bits, ||x||^2}
   void* bin_list;     // ... M-step row pass: per-tile row bins (4 B per row) and their bucket offsets
   int* bin_off;
+  const int* skip;    // nullable: device word (LoopState::done); non-zero -> every kernel of the call returns at once
+  int first_chunk;    // reduce_partials overwrites the accumulators (first chunk of an iteration) instead of adding
+  int counts_f64;     // the counts accumulator is float64 (one float64 buffer for the all-reduce) instead of int64
   double* out_sums;   // final accumulators (the re-check kernel adds the deferred rows' contributions)
   long long* out_counts;
   double* out_dist_sum;
+};
+
+// Device-resident state of a Lloyd loop (bkm_loop_reset / bkm_finalize_step): the stop test of
+// dask_ml/cluster/k_means.py:555-559 runs on the device, iterations enqueued after convergence are no-ops.
+struct LoopState {
+  int done;          // set by the iteration whose shift < tol (its centre update is NOT applied: Q3)
+  int n_iter;        // iterations executed (including the converging one)
+  int hist_cap;
+  int pad;
+  double tol;
+  double shift;      // shift of the last executed iteration
+  double* hist;      // nullable: shift of iteration i at hist[i] (i < hist_cap)
 };
 
 // implemented in bkm_simt.cu
@@ -192,6 +207,7 @@ int launch_simt(const ChunkArgs& a, bool mstep, int dtype, int sm_count, int* gr
 // implemented in bkm_tc.cu
 bool tc_supported(int d, int k, int dtype);
 int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
+int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t s);
 int tc_trace(long long* out, int n);
 // implemented in bkm_stream.cu
 bool stream_supported(int d, int k, int dtype);

@@ -74,7 +74,9 @@ template <> struct RowPiece<__nv_bfloat16, 4> {
 // One CTA per tile (grid-stride); labels are read once.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RP_THREADS)
-rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigned* __restrict__ bins, int* __restrict__ tile_off) {
+rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigned* __restrict__ bins, int* __restrict__ tile_off,
+                   const int* skip) {
+  if (skip && *skip) return;
   __shared__ int cntw[RP_NW][RP_MAXB];          // pass 1: rows of (warp, bucket); pass 2: running write position
   __shared__ int base_s[RP_MAXB + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,6 +144,8 @@ rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigne
 template <typename TX, int FPL>
 __global__ void __launch_bounds__(RP_THREADS, 1)
 rowpass_mstep_kernel(ChunkArgs a, RpCfg c, const unsigned* __restrict__ bins, const int* __restrict__ tile_off) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = a.k, d = a.d, CS = c.CS;
@@ -234,6 +238,8 @@ rowpass_mstep_kernel(ChunkArgs a, RpCfg c, const unsigned* __restrict__ bins, co
 template <typename TX>
 __global__ void __launch_bounds__(256)
 rowpass_dist_kernel(ChunkArgs a) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   __shared__ double red_s[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = a.d, d4 = a.L.d4;
@@ -301,7 +307,7 @@ int launch_rowpass_mstep(const ChunkArgs& a, int x_dtype, int sm_count, int* par
   unsigned* bins = reinterpret_cast<unsigned*>(a.bin_list);
   int* tile_off = a.bin_off;
   long long nbk = c.ntiles < (long long)sm_count * 4 ? c.ntiles : (long long)sm_count * 4;
-  rowpass_bin_kernel<<<(int)nbk, RP_THREADS, 0, s>>>(a.labels, a.n, c, bins, tile_off);
+  rowpass_bin_kernel<<<(int)nbk, RP_THREADS, 0, s>>>(a.labels, a.n, c, bins, tile_off, a.skip);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
 #define RP_GO(F)                                                                                                   \

@@ -88,6 +88,8 @@ static inline bool simt_mode_global(int k, int d, int J, bool mstep) {
 template <typename T, int J, bool MSTEP, bool GLOBAL, bool SMALLK>
 __global__ void __launch_bounds__(TILE)
 simt_chunk_kernel(ChunkArgs a, SimtSmem S) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   typedef typename PsumT<T>::type PS;
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

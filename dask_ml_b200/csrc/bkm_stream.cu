@@ -55,6 +55,8 @@ static inline StreamSmem stream_smem(int k, int d, long long ldx, int kpt, int d
 template <int DH, int KPT, bool MSTEP>
 __global__ void __launch_bounds__(SW * 32, 2)
 stream_chunk_kernel(ChunkArgs a, StreamSmem S) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   constexpr int DP = DH * 2;
   constexpr int D4 = (DP + 3) / 4;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -366,6 +368,8 @@ static inline Stream2Smem stream2_smem(int k, int d, long long ldx, int kc, int 
 template <int DH, int KC, bool MSTEP>
 __global__ void __launch_bounds__(SW * 32, 2)
 stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   constexpr int DP = DH * 2;
   constexpr int D4 = (DP + 3) / 4;
   extern __shared__ __align__(128) unsigned char smem[];

@@ -267,6 +267,8 @@ __global__ void __launch_bounds__(tc_threads(MSTEP, WANT_DIST), 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
                 const __grid_constant__ CUtensorMap tm_xm) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr bool LANE_OWNS = !(MSTEP && WANT_DIST);   // M-step flavour (see the two M-step blocks below)
   constexpr bool HAS_M = MSTEP || WANT_DIST;          // labels-only assignment has no M-step / distance stage at all
@@ -918,6 +920,8 @@ static const int RCK_ROWS = 8;      // deferred rows decided together by one CTA
 
 __global__ void __launch_bounds__(256)
 tc_recheck_kernel(ChunkArgs a, bool mstep, double* sums, unsigned long long* counts, double* dist_sum) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   __shared__ float xs[RCK_ROWS][64];
   __shared__ double wd[RCK_ROWS][8];
   __shared__ int wj[RCK_ROWS][8];
@@ -990,7 +994,10 @@ tc_recheck_kernel(ChunkArgs a, bool mstep, double* sums, unsigned long long* cou
       if (a.labels) a.labels[row] = fj;
       if (a.min_out) reinterpret_cast<float*>(a.min_out)[row] = (float)outv;
       if (dist_sum) atomicAdd(dist_sum, outv);
-      if (mstep) atomicAdd(counts + fj, 1ull);
+      if (mstep) {
+        if (a.counts_f64) atomicAdd(reinterpret_cast<double*>(counts) + fj, 1.0);
+        else atomicAdd(counts + fj, 1ull);
+      }
       wj[r][0] = fj;
     }
     __syncthreads();
@@ -1002,7 +1009,10 @@ tc_recheck_kernel(ChunkArgs a, bool mstep, double* sums, unsigned long long* cou
   }
 }
 
-static int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t s) {
+// Runs AFTER reduce_partials (which may overwrite the accumulators for the first chunk of an iteration): the deferred
+// rows' contributions are added on top.
+int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t s) {
+  if (a.k <= 1) return 0;
   tc_recheck_kernel<<<sm_count * 4, 256, 0, s>>>(a, mstep, a.out_sums, (unsigned long long*)a.out_counts, a.out_dist_sum);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
@@ -1151,12 +1161,6 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   else { if (want_dist) TC_LAUNCH(false, true) else TC_LAUNCH(false, false) }
 #undef TC_LAUNCH
   note_launch(2);
-  BKM_CUDA_TRY(cudaGetLastError());
-  if (a.k > 1) {
-    int rc2 = launch_tc_recheck(a, mstep, sm_count, s);
-    if (rc2) return rc2;
-  }
-  note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;
 }

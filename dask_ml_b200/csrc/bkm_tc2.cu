@@ -70,6 +70,8 @@ enum {
 __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_assign_kernel(ChunkArgs a, Tc2Cfg cfg, const __grid_constant__ CUtensorMap tm_x,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
@@ -314,6 +316,8 @@ tc2_assign_kernel(ChunkArgs a, Tc2Cfg cfg, const __grid_constant__ CUtensorMap t
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tc2_combine_kernel(ChunkArgs a, int S) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   const PackHeader* hdr = reinterpret_cast<const PackHeader*>(a.pack);
   const float cnmax = (float)hdr->cn_max;
   for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < a.n; row += (long long)gridDim.x * blockDim.x) {
@@ -353,6 +357,8 @@ template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __
 template <typename TX>
 __global__ void __launch_bounds__(256)
 tc2_recheck_kernel(ChunkArgs a, int kp2) {
+  if (a.skip && *a.skip) return;                            // converged loop: no-op iteration
+
   __shared__ double xs[128][R2_ROWS];            // [feature][row]: the rows of a feature are one 128-byte broadcast
   __shared__ double wd[R2_ROWS][8];
   __shared__ int wj[R2_ROWS][8];

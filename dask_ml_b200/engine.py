@@ -189,15 +189,49 @@ class CudaBackend(object):
                                                  out.numel(), self._stream()), "bkm_pack_centers")
         return out
 
-    def lloyd_chunk(self, x, pack, k, labels, min_d2, sums, counts, inertia):
+    def lloyd_chunk(self, x, pack, k, labels, min_d2, sums, counts, inertia, first=False, loop_state=None):
+        """Fused E+M step of one chunk.  ``counts`` may be int64 or float64 (one float64 buffer for the all-reduce);
+        ``first`` overwrites the accumulators instead of adding (first chunk of an iteration); ``loop_state`` makes
+        the call a no-op once the device-side loop has converged."""
         n, d = x.shape
         ws = self._workspace(n, d, k, x.dtype)
+        flags = self.flags
+        if first:
+            flags |= _lib.FLAG_FIRST_CHUNK
+        if counts is not None and counts.dtype == torch.float64:
+            flags |= _lib.FLAG_COUNTS_F64
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bkm_lloyd_chunk(
                 self._ptr(x), n, d, x.stride(0) if n else d, _DT_CODE[x.dtype], self._ptr(pack), k,
                 self._ptr(labels), self._ptr(min_d2), self._ptr(sums), self._ptr(counts),
-                self._ptr(inertia), self._ptr(ws), ws.numel(), self.flags, self._stream()),
+                self._ptr(inertia), self._ptr(ws), ws.numel(), flags, self._ptr(loop_state), self._stream()),
                 "bkm_lloyd_chunk")
+
+    # -- device-resident Lloyd loop ------------------------------------------------------
+    def loop_state_new(self, tol, max_iter):
+        """(state bytes, shift history) for one Lloyd loop, reset on the device."""
+        nb = ctypes.c_size_t(0)
+        _lib.check(self.lib.bkm_loop_state_bytes(ctypes.byref(nb)), "bkm_loop_state_bytes")
+        state = torch.zeros(int(nb.value), dtype=torch.uint8, device=self.device)
+        hist = torch.zeros(max(1, int(max_iter)), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bkm_loop_reset(self._ptr(state), float(tol), self._ptr(hist), int(hist.numel()),
+                                               self._stream()), "bkm_loop_reset")
+        return state, hist
+
+    def loop_state_read(self, state):
+        """(done, n_iter, shift) — one device->host copy (the loop's only synchronisation)."""
+        raw = state.cpu().numpy()
+        done, n_iter = np.frombuffer(raw[:8].tobytes(), dtype=np.int32)
+        shift = np.frombuffer(raw[24:32].tobytes(), dtype=np.float64)[0]
+        return int(done), int(n_iter), float(shift)
+
+    def finalize_step(self, red, c_in, c_out, state, pack, dtype):
+        k, d = c_in.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bkm_finalize_step(self._ptr(red), self._ptr(c_in), self._ptr(c_out), self._ptr(state),
+                                                  k, d, _DT_CODE[dtype], self._ptr(pack), pack.numel(), self._stream()),
+                       "bkm_finalize_step")
 
     def assign_chunk(self, x, pack, k, labels, min_dist, squared, dist_sum):
         n, d = x.shape

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define BKM_VERSION 100
+#define BKM_VERSION 200
 
 /* element types of X */
 #define BKM_F32 0
@@ -59,6 +59,10 @@ extern "C" {
 #define BKM_FLAG_FORCE_SIMT   1   /* never use the tcgen05 path (exact-fp32 CUDA-core kernel) */
 #define BKM_FLAG_FORCE_TC     2   /* fail with BKM_EUNSUPPORTED instead of falling back to SIMT */
 #define BKM_FLAG_NO_RECHECK   4   /* skip the float64 re-check of near-tie rows */
+#define BKM_FLAG_FIRST_CHUNK  8   /* bkm_lloyd_chunk: OVERWRITE sums / counts / inertia (first chunk of an iteration)
+                                     instead of accumulating: saves the memsets of the step */
+#define BKM_FLAG_COUNTS_F64  16   /* bkm_lloyd_chunk: `counts` points to float64 (so that sums | counts | inertia are ONE
+                                     float64 buffer for the per-iteration all-reduce) */
 
 int bkm_version(void);
 const char* bkm_error_string(int code);
@@ -99,7 +103,8 @@ int bkm_lloyd_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
                     const void* pack, int k,
                     int32_t* labels, void* min_d2,
                     double* sums, int64_t* counts, double* inertia,
-                    void* workspace, size_t workspace_bytes, int flags, void* stream);
+                    void* workspace, size_t workspace_bytes, int flags,
+                    const void* loop_state /* nullable, see bkm_loop_reset */, void* stream);
 
 /* ---- E-step only (predict, final re-label, k-means|| cost) ---------------------------
  * replaces: pairwise_distances_argmin_min(X, centers[, squared]) per chunk.
@@ -131,6 +136,25 @@ int bkm_transform_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtyp
  *   *shift = sum((C_old - C_new)^2)        (float64)                                  */
 int bkm_finalize(const double* sums, const int64_t* counts, const double* centers_old,
                  double* centers_new, double* shift, int k, int d, void* stream);
+
+/* ---- device-resident Lloyd loop (k_means.py:522-560 without a host round trip per iteration) -----------------
+ * The reference reads the shift back to the client every iteration (k_means.py:552-559).  Here the stop test runs on
+ * the device: a small LoopState {done, n_iter, tol, shift, shift history} lives in device memory; bkm_finalize_step
+ * updates it, and every kernel of a bkm_lloyd_chunk call that was given the state returns at once when `done` is set.
+ * The host enqueues iterations back to back and looks at the state every few iterations; iterations enqueued after
+ * convergence are no-ops, so n_iter, the centres and the labels are exactly those of the reference's loop.
+ *   bkm_loop_reset     done = 0, n_iter = 0, tol; shift_hist (device, nullable): shift of iteration i at [i]
+ *   bkm_finalize_step  replaces bkm_finalize (+ bkm_pack_centers for the next iteration):
+ *       reduced = [k*d sums | k counts as float64 | inertia]  (BKM_FLAG_COUNTS_F64; after the all-reduce)
+ *       C' = sums / max(counts, 1); shift = ||centers_in - C'||_F^2; n_iter += 1
+ *       shift < tol : done = 1, centers_out is not meaningful (the reference breaks BEFORE taking C' over, Q3)
+ *       else        : centers_out = C' and `pack` is rebuilt from C'  (centers_in != centers_out: ping-pong)
+ * Read the state back with a plain device->host copy of bkm_loop_state_bytes() bytes: {int32 done, int32 n_iter,
+ * int32 hist_cap, int32 pad, float64 tol, float64 shift, pointer}. */
+int bkm_loop_state_bytes(size_t* out);
+int bkm_loop_reset(void* loop_state, double tol, double* shift_hist, int hist_cap, void* stream);
+int bkm_finalize_step(const double* reduced, const double* centers_in, double* centers_out, void* loop_state,
+                      int k, int d, int x_dtype, void* pack, size_t pack_bytes, void* stream);
 
 /* ---- NaN/inf scan of a chunk (k_means.py:179-180): sets *flag (int32) nonzero -------- */
 int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bkm_version() == 100
+    assert lib.bkm_version() == 200
     assert lib.bkm_error_string(-3) == b"shape not supported by any kernel"
     out = ctypes.c_size_t(0)
     assert lib.bkm_centers_pack_bytes(256, 64, 0, ctypes.byref(out)) == 0 and out.value > 256 * 64 * 4
