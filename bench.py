@@ -518,6 +518,36 @@ def main():
                "api": "dask_ml_b200.cluster.k_means.lloyd_iteration_host (pinned host X, double-buffered H2D)"}
         del Xh
     fam_c2 = int(be.kernel_family(N_FEAT, N_CLUST, torch.float32))
+    # ---- KMeans.transform on C2: (n, k) float32 distances = 10.24 GB of output per pass: the HBM WRITE roof binds ----
+    xform = None
+    try:
+        tn = min(n, 4_000_000)                      # 4M x 256 float32 = 4.1 GB output block (linear in n)
+        out = torch.empty((tn, N_CLUST), dtype=torch.float32, device=dev)
+        pack = be.pack_centers(C_used, torch.float32)
+        for _ in range(2):
+            be.transform_chunk(X[:tn], pack, N_CLUST, out)
+        barrier()
+        x0 = torch.cuda.Event(enable_timing=True)
+        x1 = torch.cuda.Event(enable_timing=True)
+        x0.record()
+        reps = 5
+        for _ in range(reps):
+            be.transform_chunk(X[:tn], pack, N_CLUST, out)
+        x1.record()
+        barrier()
+        xms = x0.elapsed_time(x1) / reps
+        xb = tn * (N_CLUST * 4 + N_FEAT * 4)
+        ref = torch.sqrt(torch.clamp(((X[:4096].double()[:, None, :] - C_used[None, :, :]) ** 2).sum(-1), min=0.0))
+        xerr = float(((out[:4096].double() - ref).abs() / (1.0 + ref)).max())
+        xform = {"what": "KMeans.transform / euclidean_distances: (n, k) float32 block, %d x %d -> %d" % (tn, N_FEAT, N_CLUST),
+                 "ms": xms, "rows": tn, "samples_per_s": tn / (xms * 1e-3),
+                 "roofline": {"bound": "hbm", "achieved": xb / (xms * 1e-3) / 1e9, "peak": float(peaks["hbm_gbs"]),
+                              "unit": "GB/s", "frac": xb / (xms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]),
+                              "algorithmic": {"bytes_per_sample": N_CLUST * 4 + N_FEAT * 4}},
+                 "max_rel_err_vs_float64": xerr}
+        del out
+    except Exception as e:
+        xform = {"error": "%s: %s" % (type(e).__name__, e)}
     del st, data, X
     torch.cuda.empty_cache()
 
@@ -583,7 +613,7 @@ def main():
                    "step": "lloyd_loop() as KMeans.fit runs it: fused E+M kernel + reduce + re-check (+ all-reduce) + finalize_step (centre update, shift, device-side stop test, next pack); one host read of the loop state per 8 iterations",
                    "kernel_family": fam_c2, "final_shift": shift},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity_check": par,
-        "allreduce_us": allreduce_us, "configs": configs, "cpu_baseline": cpu,
+        "allreduce_us": allreduce_us, "transform": xform, "configs": configs, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

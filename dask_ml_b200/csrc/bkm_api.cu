@@ -16,7 +16,8 @@ int launch_finalize(const double* sums, const long long* counts, const double* C
 int launch_sample(const void* d2, long long n, int dtype, double eop, uint64_t seed, uint64_t off,
                   long long* picked, long long cap, int* n_picked, cudaStream_t s);
 int launch_transform(const void* X, long long n, int d, long long ldx, int dtype,
-                     const void* pack, int k, void* out, int sm_count, cudaStream_t s);
+                     const void* pack, int k, void* out, long long ld_out, int mode, double gamma, int sm_count,
+                     cudaStream_t s);
 int launch_check_finite(const void* X, long long n, int d, long long ldx, int dtype, int* flag,
                         int sm_count, cudaStream_t s);
 
@@ -234,15 +235,28 @@ int bkm_sample_chunk(const void* min_d2, int64_t n, int x_dtype, double ell_over
 }
 
 int bkm_transform_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
-                        const void* pack, int k, void* out, void* stream) {
-  if (n < 0 || d <= 0 || k <= 0 || ldx < d || !pack) return BKM_EINVAL;
+                        const void* pack, int k, void* out, int64_t ld_out, int mode, double gamma, int flags,
+                        void* stream) {
+  if (n < 0 || d <= 0 || k <= 0 || ldx < d || !pack || ld_out < k || mode < 0 || mode > 2) return BKM_EINVAL;
   if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
   if (n == 0) return 0;
   if (!X || !out) return BKM_EINVAL;
   int sm = 0;
   int rc = sm_count_of_current(&sm);
   if (rc) return rc;
-  return launch_transform(X, n, d, ldx, x_dtype, pack, k, out, sm, (cudaStream_t)stream);
+  // fp32, d <= 64, k <= 256: the tcgen05 pipeline with the transform epilogue (callers cut wider Y into column blocks)
+  if (x_dtype == BKM_F32 && tc_supported(d, k, x_dtype) && !(flags & BKM_FLAG_FORCE_SIMT)) {
+    ChunkArgs a = {};
+    a.X = X; a.n = n; a.d = d; a.ldx = ldx;
+    a.pack = (const unsigned char*)pack;
+    a.L = pack_layout(k, d, x_dtype);
+    a.k = k;
+    a.xf_out = (float*)out; a.xf_ld = ld_out; a.xf_mode = mode; a.xf_gamma = (float)gamma;
+    rc = launch_tc_transform(a, sm, (cudaStream_t)stream);
+    if (rc != BKM_EALIGN && rc != BKM_EUNSUPPORTED) return rc;
+    if (flags & BKM_FLAG_FORCE_TC) return rc;
+  } else if (flags & BKM_FLAG_FORCE_TC) return BKM_EUNSUPPORTED;
+  return launch_transform(X, n, d, ldx, x_dtype, pack, k, out, ld_out, mode, gamma, sm, (cudaStream_t)stream);
 }
 
 int bkm_finalize(const double* sums, const int64_t* counts, const double* centers_old,

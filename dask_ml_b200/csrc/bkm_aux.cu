@@ -626,7 +626,8 @@ int launch_sample(const void* d2, long long n, int dtype, double eop, uint64_t s
 template <typename T>
 __global__ void __launch_bounds__(256)
 transform_kernel(const T* __restrict__ X, long long n, int d, long long ldx,
-                 const unsigned char* __restrict__ pack, PackLayout L, T* __restrict__ out) {
+                 const unsigned char* __restrict__ pack, PackLayout L, T* __restrict__ out, long long ld_out, int mode,
+                 double gamma) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int TR = 64;
   const int k = L.k, d4 = L.d4;
@@ -660,13 +661,14 @@ transform_kernel(const T* __restrict__ X, long long n, int d, long long ldx,
       for (int i = 0; i < d; ++i) acc = fma(xr[i], cr[i], acc);
       T v = xn[r] + cn[j] - T(2) * acc;
       v = v > T(0) ? v : T(0);
-      out[(r0 + r) * (long long)k + j] = sqrt(v);
+      out[(r0 + r) * ld_out + j] = mode == 0 ? sqrt(v) : (mode == 1 ? v : (T)exp(-(T)gamma * v));
     }
   }
 }
 
 int launch_transform(const void* X, long long n, int d, long long ldx, int dtype,
-                     const void* pack, int k, void* out, int sm_count, cudaStream_t s) {
+                     const void* pack, int k, void* out, long long ld_out, int mode, double gamma, int sm_count,
+                     cudaStream_t s) {
   if (n == 0) return 0;
   PackLayout L = pack_layout(k, d, dtype);
   long long ntiles = (n + 63) / 64;
@@ -675,10 +677,10 @@ int launch_transform(const void* X, long long n, int d, long long ldx, int dtype
   size_t smem = (size_t)64 * (L.d4 + 1) * esz + 64 * esz + 16;
   if (dtype == BKM_F32) {
     BKM_CUDA_TRY(cudaFuncSetAttribute(transform_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    transform_kernel<float><<<(int)grid, 256, smem, s>>>((const float*)X, n, d, ldx, (const unsigned char*)pack, L, (float*)out);
+    transform_kernel<float><<<(int)grid, 256, smem, s>>>((const float*)X, n, d, ldx, (const unsigned char*)pack, L, (float*)out, ld_out, mode, gamma);
   } else {
     BKM_CUDA_TRY(cudaFuncSetAttribute(transform_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    transform_kernel<double><<<(int)grid, 256, smem, s>>>((const double*)X, n, d, ldx, (const unsigned char*)pack, L, (double*)out);
+    transform_kernel<double><<<(int)grid, 256, smem, s>>>((const double*)X, n, d, ldx, (const unsigned char*)pack, L, (double*)out, ld_out, mode, gamma);
   }
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());

@@ -182,6 +182,10 @@ struct ChunkArgs {
   float4* rec;        // large-shape tensor path: [S][n] partial arg-min records {m1, m2, label bits, ||x||^2}
   void* bin_list;     // ... M-step row pass: per-tile row bins (4 B per row) and their bucket offsets
   int* bin_off;
+  float* xf_out;      // transform variants: output block (rows x k), row pitch xf_ld floats; mode 0 sqrt / 1 squared / 2 rbf
+  long long xf_ld;
+  int xf_mode;
+  float xf_gamma;
   const int* skip;    // nullable: device word (LoopState::done); non-zero -> every kernel of the call returns at once
   int first_chunk;    // reduce_partials overwrites the accumulators (first chunk of an iteration) instead of adding
   int counts_f64;     // the counts accumulator is float64 (one float64 buffer for the all-reduce) instead of int64
@@ -208,6 +212,7 @@ int launch_simt(const ChunkArgs& a, bool mstep, int dtype, int sm_count, int* gr
 bool tc_supported(int d, int k, int dtype);
 int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaStream_t s);
 int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t s);
+int launch_tc_transform(const ChunkArgs& a, int sm_count, cudaStream_t s);
 int tc_trace(long long* out, int n);
 // implemented in bkm_stream.cu
 bool stream_supported(int d, int k, int dtype);

@@ -262,7 +262,9 @@ __device__ __forceinline__ uint32_t sw_chunk(int r, int q) { return (uint32_t)(r
 
 #define ACC32_CASE(j) case j: acc[j][0] += x0; acc[j][1] += x1; break;
 
-template <bool MSTEP, bool WANT_DIST>
+// XFORM: the epilogue writes the whole (rows x k) block of distances / kernel values instead of the arg-min
+// (euclidean_distances, dask_ml/metrics/pairwise.py:69-97; rbf_kernel :131-139) — same pipeline, no M-step warps' work.
+template <bool MSTEP, bool WANT_DIST, bool XFORM = false>
 __global__ void __launch_bounds__(tc_threads(MSTEP, WANT_DIST), 1)
 tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
@@ -575,6 +577,53 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       // saved chunk is scanned once: every element within `bound` of m1 adds (1 + i/1024) to an accumulator:
       //   exactly one hit  -> 1 + i/1024 : the arg-min, decoded exactly
       //   two or more hits (or m2 within the bound) -> near-tie, the row is deferred to float64
+      if (XFORM) {
+        // d^2 = (acc + ||s x||^2) / s^2, clamped at 0; mode 0: sqrt, 1: squared, 2: exp(-gamma d^2).  Thread = row: every
+        // 16-column chunk is 64 contiguous bytes of the output row (four 16-byte stores when the row is 16-byte aligned).
+        const float sc = hdr->scale;
+        const float inv_s2 = 1.0f / (sc * sc);
+        const long long row = tile * BM + r;
+        const bool valid = row < a.n;
+        float* orow = a.xf_out + (valid ? row : 0) * a.xf_ld;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(a.xf_out) & 15) == 0) && ((a.xf_ld & 3) == 0);
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+          const long long g = it * U + u;
+          const int buf = (int)(g % NBUF);
+          const int nch = (u == 0 ? cfg.NU0 : cfg.NU1) >> 4;
+          const int col0 = u == 0 ? 0 : cfg.NU0;
+          mbar_wait(BAR(BAR_ACC_FULL + set * NBUF + buf), acc_parity(g, U));
+          tc_fence_after();
+          const uint32_t tbase = tmem + lane_addr + (uint32_t)buf * 128u;
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c) {
+            uint32_t v[16];
+            TC_LD16(tbase + (uint32_t)c * 16u, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float d2 = fmaxf((__uint_as_float(v[i]) + xn) * inv_s2, 0.f);
+              o[i] = a.xf_mode == 0 ? sqrtf(d2) : (a.xf_mode == 1 ? d2 : __expf(-a.xf_gamma * d2));
+            }
+            const int cb = col0 + c * 16;
+            if (valid) {
+              if (vec_ok && cb + 16 <= a.k) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  __stcs(reinterpret_cast<float4*>(orow + cb) + q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (cb + i < a.k) orow[cb + i] = o[i];
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(BAR(BAR_ACC_EMPTY + 2 * (set * NBUF + buf) + (int)((g + NBUF) & 1)));
+        }
+        continue;
+      }
       float m1 = CUDART_INF_F, m2 = CUDART_INF_F, sbase = 0.f;
       float sv[16];
 #pragma unroll
@@ -900,7 +949,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
   if (tid == 0) {
     double t = red_s[NMWK];
     for (int w = 0; w < NMWK; ++w) t += red_s[w];
-    a.pin[blockIdx.x] = t;
+    if (a.pin) a.pin[blockIdx.x] = t;             // (the transform variant has no per-CTA partials)
   }
   if (warp == 0) {
     __syncwarp();
@@ -1020,6 +1069,7 @@ int launch_tc_recheck(const ChunkArgs& a, bool mstep, int sm_count, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------ host
+int launch_tc_transform(const ChunkArgs& a, int sm_count, cudaStream_t s);
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1161,6 +1211,31 @@ int launch_tc(const ChunkArgs& a, bool mstep, int sm_count, int* grid_out, cudaS
   else { if (want_dist) TC_LAUNCH(false, true) else TC_LAUNCH(false, false) }
 #undef TC_LAUNCH
   note_launch(2);
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// (rows x k) block of distances / kernel values on the tensor path: same kernel, transform epilogue
+int launch_tc_transform(const ChunkArgs& a, int sm_count, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(a.X) & 15) || (a.ldx % 4)) return BKM_EALIGN;
+  TcCfg cfg;
+  if (!make_cfg(a.d, a.k, false, false, &cfg)) return BKM_EUNSUPPORTED;
+  CUtensorMap tm_x, tm_bhi, tm_blo, tm_xm;
+  int rc = make_map(&tm_x, a.X, a.n, a.d, a.ldx, BM);
+  if (rc) return rc;
+  rc = make_map(&tm_xm, a.X, a.n, a.d, a.ldx, cfg.MR);
+  if (rc) return rc;
+  rc = make_map(&tm_bhi, a.pack + a.L.off_bhi, a.L.kp, a.L.dh, a.L.dh, cfg.NP, true);
+  if (rc) return rc;
+  rc = make_map(&tm_blo, a.pack + a.L.off_blo, a.L.kp, a.L.dh, a.L.dh, cfg.NP, true);
+  if (rc) return rc;
+  long long ntiles = (a.n + BM - 1) / BM;
+  int grid = (int)(ntiles < sm_count ? ntiles : sm_count);
+  if (grid < 1) grid = 1;
+  auto kern = tc_chunk_kernel<false, false, true>;
+  BKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.total));
+  kern<<<grid, tc_threads(false, false), cfg.total, s>>>(a, cfg, tm_x, tm_bhi, tm_blo, tm_xm);
+  note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
   return 0;
 }

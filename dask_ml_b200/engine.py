@@ -249,12 +249,15 @@ class CudaBackend(object):
                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(row_offset), self._ptr(picked), picked.numel(),
                 self._ptr(n_picked), self._stream()), "bkm_sample_chunk")
 
-    def transform_chunk(self, x, pack, k, out):
+    def transform_chunk(self, x, pack, k, out, mode=0, gamma=0.0):
+        """(n, k) block of distances (mode 0), squared distances (1) or exp(-gamma d^2) (2) into ``out`` — which may be a
+        column block of a wider matrix (row pitch = out.stride(0))."""
         n, d = x.shape
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bkm_transform_chunk(
                 self._ptr(x), n, d, x.stride(0) if n else d, _DT_CODE[x.dtype], self._ptr(pack), k,
-                self._ptr(out), self._stream()), "bkm_transform_chunk")
+                self._ptr(out), out.stride(0) if n else k, int(mode), float(gamma), self.flags, self._stream()),
+                "bkm_transform_chunk")
 
     def finalize(self, sums, counts, C_old, C_new, shift):
         k, d = C_old.shape

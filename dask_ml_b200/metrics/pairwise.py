@@ -58,42 +58,141 @@ def pairwise_distances(X, Y, metric="euclidean", n_jobs=None, **kwargs):
     return euclidean_distances(X, Y)
 
 
+def _distance_blocks(X, Y, mode, gamma=0.0):
+    """(n_i, len(Y)) blocks of distances / squared distances / rbf values, one per chunk of X.  Y wider than 256 rows is
+    cut into column blocks of 256 (the width of the tensor-path kernel); every block is one pass of the chunk."""
+    be = X.backend
+    Y64 = np.ascontiguousarray(Y, dtype=np.float64)
+    k = int(Y64.shape[0])
+    step = 256
+    outs = [be.empty((int(x.shape[0]), k), X.dtype) for x in X.chunks]
+    for c0 in range(0, k, step):
+        c1 = min(k, c0 + step)
+        C = torch.as_tensor(Y64[c0:c1]).to(be.device)
+        pack = be.pack_centers(C, X.dtype)
+        for x, out in zip(X.chunks, outs):
+            if int(x.shape[0]):
+                be.transform_chunk(x, pack, c1 - c0, out[:, c0:c1], mode=mode, gamma=gamma)
+    return outs
+
+
+def _as_device(X):
+    from ..cluster.k_means import _to_device_data
+    from ..engine import DeviceData
+
+    X = _to_device_data(X, check_finite=False)
+    if X.dtype == torch.bfloat16:
+        # the full distance matrix of bf16 rows is produced in float32 (no bf16 transform kernel)
+        X = DeviceData([c.to(torch.float32) for c in X.chunks], X.backend, X.comm)
+    return X
+
+
 def euclidean_distances(X, Y=None, Y_norm_squared=None, squared=False, X_norm_squared=None):
     """sqrt(max(||x||^2 - 2 x.y + ||y||^2, 0)) for every (row of X, row of Y)  (pairwise.py:69-97).
 
-    The result has the dtype of X.  ``X_norm_squared`` / ``Y_norm_squared`` are validated for
-    shape as in the reference but the kernel recomputes the norms on the fly (they are free).
+    The result has the dtype of X (float64 when Y is float64, like ``-2 * dot(X, Y.T) + XX + YY`` in the reference).
+    ``Y=None`` means X against itself.  The kernels compute the row norms themselves; when ``X_norm_squared`` /
+    ``Y_norm_squared`` are passed they are validated AND used as the reference uses them (pairwise.py:72-91): the
+    difference to the true norms is added to the squared distances before the clamp / square root.
     """
+    from ..engine import DeviceData
+
+    X = _as_device(X)
     if Y is None:
-        raise NotImplementedError("Y=None (X against itself) is not on the KMeans path")
-    from ..cluster.k_means import _to_device_data
-
-    X = _to_device_data(X, check_finite=False)
+        Y = X.to_host()
     Y = np.asarray(Y)
-    if X.dtype == torch.bfloat16:
-        # the full distance matrix of bf16 rows is produced in float32 (no bf16 transform kernel)
-        from ..engine import DeviceData
-
-        X = DeviceData([c.to(torch.float32) for c in X.chunks], X.backend, X.comm)
+    if Y.ndim != 2 or Y.shape[1] != X.d:
+        raise ValueError(
+            "Incompatible dimension for X and Y matrices: X.shape[1] == %d while Y.shape[1] == %d"
+            % (X.d, Y.shape[1] if Y.ndim == 2 else -1)
+        )
     if X.dtype == torch.float32 and Y.dtype == np.float64:
         # result dtype follows numpy promotion of (X, Y) like -2*dot(X, Y.T)+XX+YY in the reference
-        from ..engine import DeviceData
-
         X = DeviceData([c.to(torch.float64) for c in X.chunks], X.backend, X.comm)
-    X, be, pack, k = _prep(X, Y)
+    k = int(Y.shape[0])
+    XXg = YYg = None
     if X_norm_squared is not None:
-        XX = np.asarray(X_norm_squared)
-        if XX.shape not in ((1, X.n_local), (X.n_local, 1)):
+        XXg = np.asarray(X_norm_squared)
+        if XXg.shape == (1, X.n_local):
+            XXg = XXg.T
+        elif XXg.shape != (X.n_local, 1):
             raise ValueError("Incompatible dimensions for X and X_norm_squared")
     if Y_norm_squared is not None:
-        YY = np.asarray(Y_norm_squared)
-        if YY.ndim < 2:
-            YY = YY[:, np.newaxis]
-        if YY.shape != (1, k):
+        YYg = np.asarray(Y_norm_squared)
+        if YYg.ndim < 2:
+            YYg = YYg[np.newaxis, :]
+        if YYg.shape == (k, 1):
+            YYg = YYg.T
+        if YYg.shape != (1, k):
             raise ValueError("Incompatible dimensions for Y and Y_norm_squared")
-    outs = []
-    for x in X.chunks:
-        out = be.empty((int(x.shape[0]), k), X.dtype)
-        be.transform_chunk(x, pack, k, out)
-        outs.append(out * out if squared else out)
-    return ChunkedArray(outs)
+    if XXg is None and YYg is None:
+        return ChunkedArray(_distance_blocks(X, Y, 1 if squared else 0))
+    # caller-supplied norms: start from the true squared distances and swap the norm terms
+    outs = _distance_blocks(X, Y, 1)
+    be = X.backend
+    Yd = torch.as_tensor(np.ascontiguousarray(Y, dtype=np.float64)).to(be.device)
+    yy_true = (Yd * Yd).sum(1)
+    off = 0
+    res = []
+    for x, out in zip(X.chunks, outs):
+        n = int(x.shape[0])
+        d2 = out.to(torch.float64)
+        if XXg is not None:
+            xx_true = (x.to(torch.float64) ** 2).sum(1)
+            d2 = d2 + (torch.as_tensor(np.asarray(XXg[off:off + n, 0], dtype=np.float64)).to(be.device) - xx_true)[:, None]
+        if YYg is not None:
+            d2 = d2 + (torch.as_tensor(np.asarray(YYg[0], dtype=np.float64)).to(be.device) - yy_true)[None, :]
+        d2 = torch.clamp(d2, min=0.0)
+        res.append((d2 if squared else torch.sqrt(d2)).to(X.dtype))
+        off += n
+    return ChunkedArray(res)
+
+
+def check_pairwise_arrays(X, Y, precomputed=False):
+    """Shape validation of pairwise.py:100-118 (Y=None means X against itself)."""
+    Xs = X.shape
+    if Y is None:
+        Y = X
+    Ys = Y.shape
+    if precomputed:
+        if Xs[1] != Ys[0]:
+            raise ValueError(
+                "Precomputed metric requires shape (n_queries, n_indexed). Got (%d, %d) for %d indexed."
+                % (Xs[0], Xs[1], Ys[0])
+            )
+    elif Xs[1] != Ys[1]:
+        raise ValueError(
+            "Incompatible dimension for X and Y matrices: X.shape[1] == %d while Y.shape[1] == %d" % (Xs[1], Ys[1])
+        )
+    return X, Y
+
+
+def rbf_kernel(X, Y=None, gamma=None):
+    """exp(-gamma * ||x - y||^2) (pairwise.py:131-139); ``gamma`` defaults to 1 / n_features.  One fused pass: the
+    distance kernel's epilogue applies the exponential (mode 2 of ``bkm_transform_chunk``)."""
+    Xd = _as_device(X)
+    if Y is None:
+        Y = Xd.to_host()
+    Y = np.asarray(Y)
+    if Y.ndim != 2 or Y.shape[1] != Xd.d:
+        raise ValueError(
+            "Incompatible dimension for X and Y matrices: X.shape[1] == %d while Y.shape[1] == %d"
+            % (Xd.d, Y.shape[1] if Y.ndim == 2 else -1)
+        )
+    if gamma is None:
+        gamma = 1.0 / Xd.d
+    return ChunkedArray(_distance_blocks(Xd, Y, 2, float(gamma)))
+
+
+def pairwise_kernels(X, Y=None, metric="linear", filter_params=False, n_jobs=1, **kwds):
+    """pairwise.py:172-195; only the kernel built on the distance path ('rbf') runs on the engine."""
+    if metric == "precomputed":
+        X, _ = check_pairwise_arrays(X, Y, precomputed=True)
+        return X
+    if metric == "rbf":
+        if filter_params:
+            kwds = dict((k, kwds[k]) for k in kwds if k in ("gamma",))
+        return rbf_kernel(X, Y, **kwds)
+    if metric in ("linear", "polynomial", "sigmoid"):
+        raise NotImplementedError("kernel %r is outside the KMeans hot path of the B200 engine" % metric)
+    raise ValueError("Unknown kernel %r" % metric)

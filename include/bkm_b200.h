@@ -126,10 +126,15 @@ int bkm_sample_chunk(const void* min_d2, int64_t n, int x_dtype,
                      double ell_over_phi, uint64_t seed, uint64_t row_offset,
                      int64_t* picked, int64_t cap, int* n_picked, void* stream);
 
-/* ---- transform: full (n,k) euclidean distance block (pairwise.py:69-97) ---------------
- * out [n*k] x-dtype, row-major: sqrt(max(||x||^2 - 2 x.c + ||c||^2, 0)). */
+/* ---- transform: full (n,k) block of distances / kernel values -------------------------------------------------
+ * replaces per chunk: metrics.euclidean_distances(X, Y[, squared])  pairwise.py:69-97  (KMeans.transform k_means.py:207-210)
+ *                     metrics.rbf_kernel(X, Y, gamma) = exp(-gamma * d^2)  pairwise.py:131-139
+ *   out [n][ld_out] x-dtype, row-major, ld_out >= k (so that callers can fill column blocks of a wider matrix):
+ *   mode 0: sqrt(max(||x||^2 - 2 x.c + ||c||^2, 0))   mode 1: the squared distance   mode 2: exp(-gamma * d^2)
+ * fp32 with d <= 64, k <= 256 runs on the tcgen05 pipeline (transform epilogue); other shapes on the CUDA cores. */
 int bkm_transform_chunk(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
-                        const void* pack, int k, void* out, void* stream);
+                        const void* pack, int k, void* out, int64_t ld_out, int mode, double gamma, int flags,
+                        void* stream);
 
 /* ---- centre update + shift (k_means.py:548-555), run after the cross-GPU allreduce ----
  *   C_new = sums / max(counts,1)[:,None]   (empty cluster -> zero vector, Q1)

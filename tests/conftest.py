@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# scikit-learn's OpenMP reductions (the oracle's E-step) on a 100+-thread GPU host next to CUDA contexts: one test order
+# segfaulted inside sklearn's ArgKmin with the default (all cores) thread count; a bounded pool is plenty for the
+# oracle's small cases.  Must be set before numpy / scikit-learn are imported.
+os.environ.setdefault("OMP_NUM_THREADS", "16")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "16")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
