@@ -260,6 +260,7 @@ def k_init(
     random_state=None,
     max_iter=None,
     oversampling_factor=2,
+    weighted=False,
 ):
     """Choose the initial centres (k_means.py:291-369).  Returns np.ndarray (k, d)."""
     n_features = X.d if isinstance(X, DeviceData) else X.shape[1]
@@ -288,7 +289,7 @@ def k_init(
         random_state = _as_random_state(random_state, X.comm)
 
     if init == "k-means||":
-        return init_scalable(X, n_clusters, random_state, max_iter, oversampling_factor)
+        return init_scalable(X, n_clusters, random_state, max_iter, oversampling_factor, weighted=weighted)
     elif init == "k-means++":
         return init_pp(X, n_clusters, random_state)
     else:
@@ -350,18 +351,60 @@ class _AssignPass(object):
 
 
 @_timed(_logger=logger)
-def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_factor=2):
+def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_factor=2, weighted=False):
     """k-means|| (Bahmani et al. 2012, Alg. 2) following k_means.py:396-463.
 
-    Each round is one distance sweep on the device (``bkm_assign_chunk``: min d^2 per row and
-    the cost phi) followed by the Bernoulli draw kernel (``bkm_sample_chunk``).  The reference
-    draws U with dask's per-chunk RandomState (k_means.py:487); here U comes from a counter-based
-    Philox stream keyed by a per-round seed and the global row index, so a run is reproducible
-    for a given ``random_state`` independent of chunking and of the number of GPUs.
+    Each round is one distance sweep on the device over the NEW candidates only (``bkm_assign_chunk``: min d^2 per
+    row), folded into the running minimum and summed to the cost phi by ``bkm_min_fold_chunk``, followed by the
+    Bernoulli draw kernel (``bkm_sample_chunk``).  The reference draws U with dask's per-chunk RandomState
+    (k_means.py:487); here U comes from a counter-based Philox stream keyed by a per-round seed and the global row
+    index, so a run is reproducible for a given ``random_state`` independent of chunking and of the number of GPUs
+    (k-means|| sampling parity with the reference is therefore distributional, not bit-exact: SURVEY.md §8c).
+
+    The final reduce of the candidates to ``n_clusters`` centres (k_means.py:457-463: an in-memory scikit-learn KMeans,
+    unweighted) runs on the GPU through this engine (``_reduce_candidates``).  ``weighted=True`` gives every candidate
+    the number of points it attracts, as the paper's step 7 does and the reference omits.
     """
     logger.info("Initializing with k-means||")
     be, comm = X.backend, X.comm
     rs = random_state if isinstance(random_state, np.random.RandomState) else _as_random_state(random_state, comm)
+    c_idx = _scalable_candidates(X, rs, max_iter, oversampling_factor)
+    sweep = _AssignPass(X)
+    # sorted, like the reference (k_means.py:432-435); fetched once, after the last round
+    centers = X.global_rows(c_idx)
+
+    if len(centers) < n_clusters:
+        logger.warning("Found fewer than %d clusters in init.", n_clusters)
+        # supplement with random rows (k_means.py:445-455).  The reference permutes all n row indices for this
+        # (random_state.choice(arange(n), replace=False)): O(n) host work for a handful of rows.  Same distribution in
+        # O(need): draw, de-duplicate, repeat.
+        need = n_clusters - len(centers)
+        n = int(X.n_global)
+        chosen = set()
+        while len(chosen) < need:
+            for v in rs.randint(0, n, size=2 * (need - len(chosen)) + 8):
+                if len(chosen) < need:
+                    chosen.add(int(v))
+        locs = sorted(chosen)
+        extra = X.global_rows(locs)
+        return np.vstack([centers, extra])
+    else:
+        # Steps 7, 8 (k_means.py:457-463): reduce the candidates to n_clusters centres
+        weights = None
+        if weighted:
+            lab, _, _ = sweep.run(centers.astype(np.float64), want_labels=True)
+            wt = be.zeros((len(centers),), torch.float64)
+            for l in lab:
+                wt += torch.bincount(l.long(), minlength=len(centers)).to(torch.float64)
+            comm.allreduce_sum_(wt)
+            weights = wt.cpu().numpy()
+        rng2 = int(rs.randint(0, 2 ** 32 - 1, dtype=np.int64))
+        return _reduce_candidates(centers, n_clusters, rng2, be, weights)
+
+
+def _scalable_candidates(X, rs, max_iter, oversampling_factor):
+    """Steps 1-6 of k-means|| (k_means.py:406-435): the sorted global row indices of the candidate centres."""
+    be, comm = X.backend, X.comm
     sweep = _AssignPass(X)
 
     # Step 1: first centre = global row 0 (k_means.py:406-408)
@@ -370,8 +413,7 @@ def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_
     c_idx = {idx}
 
     # Step 2: initial cost (k_means.py:411-420)
-    _, _, cost_t = sweep.run(centers.astype(np.float64), squared=True)
-    cost = float(cost_t.item())
+    cost = sweep.cost(centers.astype(np.float64))
     if cost == 0:
         n_iter = 0
     else:
@@ -389,17 +431,28 @@ def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_
         with _timer("init iteration %2d/%2d , %2d centers" % (i + 1, n_iter, len(c_idx)), _logger=logger):
             seed = int(rs.randint(0, 2 ** 31 - 1)) | (int(rs.randint(0, 2 ** 31 - 1)) << 32)
             fresh = sorted(c_idx - swept)
-            for b0 in range(0, len(fresh), 256):
-                block = X.global_rows(fresh[b0:b0 + 256]).astype(np.float64)
+            phi_t = be.zeros((1,), torch.float64)
+            blocks = [fresh[b0:b0 + 256] for b0 in range(0, len(fresh), 256)]
+            for bi, blk in enumerate(blocks):
+                block = X.global_rows(blk).astype(np.float64)
                 _, mins_b, _ = sweep.run(block, want_min=True, squared=True)
-                run_min = mins_b if run_min is None else [torch.minimum(a, b) for a, b in zip(run_min, mins_b)]
+                last = bi == len(blocks) - 1
+                if run_min is None:
+                    run_min = mins_b
+                    if last:
+                        for a in run_min:
+                            be.min_fold(a, None, phi_t)
+                else:
+                    for a, b in zip(run_min, mins_b):
+                        be.min_fold(a, b, phi_t if last else None)      # phi from the fully folded minimum only
+            if not blocks:
+                for a in run_min:
+                    be.min_fold(a, None, phi_t)
             swept |= set(fresh)
             mins = run_min
-            phi_t = be.zeros((1,), torch.float64)
-            for mn in mins:
-                phi_t += mn.sum(dtype=torch.float64)
             comm.allreduce_sum_(phi_t)
             phi = float(phi_t.item())
+            _check_engine(be, phi, "the k-means|| cost")
             new_idxs = set()
             if phi > 0:
                 cap = max(1024, 8 * int(oversampling_factor) + 1024)
@@ -407,9 +460,9 @@ def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_
                     picked = be.empty((cap,), torch.int64)
                     n_picked = be.zeros((1,), torch.int32)
                     off = X.row_offset
-                    for x, mn in zip(X.chunks, mins):
+                    for rows, mn in zip(X.chunk_rows, mins):
                         be.sample_chunk(mn, oversampling_factor / phi, seed, off, picked, n_picked)
-                        off += int(x.shape[0])
+                        off += int(rows)
                     m = int(n_picked.item())
                     if m <= cap:
                         break
@@ -418,25 +471,90 @@ def init_scalable(X, n_clusters, random_state=None, max_iter=None, oversampling_
                 for part in comm.allgather_obj(local):
                     new_idxs |= set(int(v) for v in part)
             c_idx |= new_idxs
-    # sorted, like the reference (k_means.py:432-435); fetched once, after the last round
-    centers = X.global_rows(sorted(c_idx))
+    return sorted(c_idx)
 
-    if len(centers) < n_clusters:
-        logger.warning("Found fewer than %d clusters in init.", n_clusters)
-        # supplement with random rows (k_means.py:445-455)
-        need = n_clusters - len(centers)
-        locs = sorted(rs.choice(np.arange(0, X.n_global), size=need, replace=False))
-        extra = X.global_rows(locs)
-        return np.vstack([centers, extra])
-    else:
-        # Steps 7, 8 without weights (k_means.py:457-463): the few candidates are reduced to k
-        # centres by an in-memory KMeans on the host, as the reference does with scikit-learn.
-        from sklearn.cluster import KMeans as _SKKMeans
 
-        rng2 = int(rs.randint(0, 2 ** 32 - 1, dtype=np.int64))
-        km = _SKKMeans(n_clusters, random_state=rng2, n_init=10)
-        km.fit(centers)
-        return km.cluster_centers_
+def _reduce_candidates(cand, n_clusters, seed, be, weights=None, n_init=10, max_iter=300, tol=1e-4):
+    """KMeans on the (few) k-means|| candidates, on the GPU: the stand-in for the in-memory scikit-learn KMeans of
+    k_means.py:457-463 (``n_init`` restarts of k-means++ seeding + Lloyd, best inertia wins, scikit-learn's
+    variance-scaled tolerance).  Runs identically on every rank (same candidates, same seed): no collective.
+    Distances go through ``bkm_assign_chunk`` / the fused Lloyd kernels; the D^2 sampling and, for the weighted
+    variant only, the weighted centre update are a few vector operations on the (m,) / (m, d) candidate arrays."""
+    from ..engine import Comm, DeviceData
+
+    cand = np.ascontiguousarray(cand)
+    m, d = cand.shape
+    dt = torch.float64 if cand.dtype == np.float64 else torch.float32
+    Xc = DeviceData([be.to_device(cand, dt)], be, _LocalComm())
+    x = Xc.chunks[0]
+    g = torch.Generator(device=be.device)
+    g.manual_seed(int(seed) & 0x7FFFFFFFFFFFFFFF)
+    w = None if weights is None else torch.as_tensor(np.asarray(weights, dtype=np.float64)).to(be.device).clamp_(min=0.0)
+    var_tol = float(np.mean(np.var(cand.astype(np.float64), axis=0)) * tol)       # sklearn's _tolerance
+    best = None
+    for _ in range(int(n_init)):
+        # ---- k-means++ seeding (D^2 sampling) over the candidates
+        first = int(torch.randint(0, m, (1,), generator=g, device=be.device).item()) if w is None else \
+            int(torch.multinomial(w / w.sum(), 1, generator=g).item())
+        chosen = [first]
+        closest = be.empty((m,), Xc.out_dtype)
+        c1 = x[first:first + 1].to(torch.float64)
+        be.assign_chunk(x, be.pack_centers(c1.contiguous(), dt), 1, None, closest, True, None)
+        for _j in range(1, n_clusters):
+            p = closest.to(torch.float64)
+            if w is not None:
+                p = p * w
+            tot = float(p.sum().item())
+            nxt = int(torch.multinomial(p / tot, 1, generator=g).item()) if tot > 0 else \
+                int(torch.randint(0, m, (1,), generator=g, device=be.device).item())
+            chosen.append(nxt)
+            newd = be.empty((m,), Xc.out_dtype)
+            be.assign_chunk(x, be.pack_centers(x[nxt:nxt + 1].to(torch.float64).contiguous(), dt), 1, None, newd, True, None)
+            be.min_fold(closest, newd, None)
+        C0 = x[torch.as_tensor(chosen, device=be.device)].to(torch.float64).cpu().numpy()
+        # ---- Lloyd on the candidates
+        if w is None:
+            st = LloydState(Xc, C0)
+            lloyd_loop(st, max_iter, var_tol)
+            inertia = float(st.relabel(squared=True).item())
+            C = st.C.cpu().numpy()
+        else:
+            C = torch.as_tensor(C0).to(be.device)
+            lab = be.empty((m,), torch.int32)
+            inertia = None
+            for _it in range(max_iter):
+                be.assign_chunk(x, be.pack_centers(C.contiguous(), dt), n_clusters, lab, None, True, None)
+                l64 = lab.long()
+                sums = torch.zeros((n_clusters, d), dtype=torch.float64, device=be.device).index_add_(
+                    0, l64, x.to(torch.float64) * w[:, None])
+                cw = torch.zeros((n_clusters,), dtype=torch.float64, device=be.device).index_add_(0, l64, w)
+                Cn = torch.where(cw[:, None] > 0, sums / cw.clamp(min=1e-300)[:, None], C)
+                shift = float(((C - Cn) ** 2).sum().item())
+                C = Cn
+                if shift <= var_tol:
+                    break
+            dmin = be.empty((m,), Xc.out_dtype)
+            be.assign_chunk(x, be.pack_centers(C.contiguous(), dt), n_clusters, lab, dmin, True, None)
+            inertia = float((dmin.to(torch.float64) * w).sum().item())
+            C = C.cpu().numpy()
+        if best is None or inertia < best[0]:
+            best = (inertia, C)
+    return best[1]
+
+
+class _LocalComm(object):
+    """Single-rank communicator for work every rank repeats identically (the candidate reduce)."""
+
+    rank, world = 0, 1
+
+    def allreduce_sum_(self, t):
+        return t
+
+    def allgather_obj(self, obj):
+        return [obj]
+
+    def bcast_obj(self, obj, src=0):
+        return obj
 
 
 def evaluate_cost(X, centers):
@@ -479,7 +597,7 @@ class LloydState(object):
         self.inertia = self.red[k * d + k:]
         self.counts = be.zeros((k,), torch.int64)
         self.shift = be.zeros((1,), torch.float64)
-        self.labels = [be.empty((int(x.shape[0]),), torch.int32) for x in X.chunks]
+        self.labels = [be.empty((m,), torch.int32) for m in X.chunk_rows]
         self.pack = None
         self.device_loop = hasattr(be, "finalize_step")
         self.kernel_event_hook = None        # bench.py: () -> (start_event, end_event) around the chunk kernels
@@ -520,7 +638,8 @@ class LloydState(object):
         be, X, k = self.be, self.X, self.k
         state, hist = be.loop_state_new(tol, max_iter)
         self.pack = be.pack_centers(self.C, X.dtype, out=self.pack)       # iteration 0's pack; later ones come from finalize_step
-        work = [(x, lab) for x, lab in zip(X.chunks, self.labels) if int(x.shape[0]) > 0]
+        resident = isinstance(X.chunks, list)
+        work = [(x, lab) for x, lab in zip(X.chunks, self.labels) if int(x.shape[0]) > 0] if resident else None
         base = self.cur
         issued = 0
         done = n_iter = 0
@@ -532,11 +651,16 @@ class LloydState(object):
                 ev = self.kernel_event_hook() if self.kernel_event_hook is not None else None
                 if ev is not None:
                     ev[0].record()
-                if not work:
+                if X.n_local == 0:
                     self.red.zero_()                  # a rank without rows still takes part in the all-reduce
-                for j, (x, lab) in enumerate(work):
-                    be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts_f, None, first=(j == 0),
+                first = True
+                # resident chunks: the prepared list; host-resident data: one streamed sweep per iteration
+                for x, lab in (work if resident else zip(X.chunks, self.labels)):
+                    if int(x.shape[0]) == 0:
+                        continue
+                    be.lloyd_chunk(x, self.pack, k, lab, None, self.sums, self.counts_f, None, first=first,
                                    loop_state=state)
+                    first = False
                 if ev is not None:
                     ev[1].record()
                 X.comm.allreduce_sum_(self.red)

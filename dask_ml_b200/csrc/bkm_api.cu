@@ -8,6 +8,9 @@ unsigned int tc_abort_code();
 void tc_abort_detail(unsigned int* out64);
 void tc_abort_reset();
 int launch_pack(const double* C, int k, int d, int dtype, void* pack, cudaStream_t s);
+int launch_make_blobs(void* X, long long* y, long long n, int d, long long ldx, int dtype, const double* centers,
+                      const double* stds, int k, uint64_t seed, int sm_count, cudaStream_t s);
+int launch_min_fold(void* run_min, const void* new_min, long long n, int dtype, double* phi_acc, int sm_count, cudaStream_t s);
 int launch_loop_reset(void* state, double tol, double* hist, int hist_cap, cudaStream_t s);
 int launch_finalize_step(const double* red, const double* c_in, double* c_out, void* state, int k, int d, int dtype,
                          void* pack, cudaStream_t s);
@@ -264,6 +267,29 @@ int bkm_finalize(const double* sums, const int64_t* counts, const double* center
   if (!sums || !counts || !centers_old || !centers_new || !shift || k <= 0 || d <= 0) return BKM_EINVAL;
   return launch_finalize(sums, (const long long*)counts, centers_old, centers_new, shift, k, d,
                          (cudaStream_t)stream);
+}
+
+int bkm_min_fold_chunk(void* run_min, const void* new_min, int64_t n, int x_dtype, double* phi_acc, void* stream) {
+  if (n < 0) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (n == 0) return 0;
+  if (!run_min) return BKM_EINVAL;
+  int sm = 0;
+  int rc = sm_count_of_current(&sm);
+  if (rc) return rc;
+  return launch_min_fold(run_min, new_min, n, x_dtype, phi_acc, sm, (cudaStream_t)stream);
+}
+
+int bkm_make_blobs_chunk(void* X, int64_t* y, int64_t n, int d, int64_t ldx, int x_dtype, const double* centers,
+                         const double* cluster_std, int k, uint64_t seed, void* stream) {
+  if (n < 0 || d <= 0 || k <= 0 || ldx < d || !centers || !cluster_std) return BKM_EINVAL;
+  if (x_dtype != BKM_F32 && x_dtype != BKM_F64) return BKM_EDTYPE;
+  if (n == 0) return 0;
+  if (!X) return BKM_EINVAL;
+  int sm = 0;
+  int rc = sm_count_of_current(&sm);
+  if (rc) return rc;
+  return launch_make_blobs(X, (long long*)y, n, d, ldx, x_dtype, centers, cluster_std, k, seed, sm, (cudaStream_t)stream);
 }
 
 int bkm_loop_state_bytes(size_t* out) {

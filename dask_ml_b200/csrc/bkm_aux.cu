@@ -688,6 +688,120 @@ int launch_transform(const void* X, long long n, int d, long long ldx, int dtype
 }
 
 // ---------------------------------------------------------------------------------------
+// k-means|| rounds (k_means.py:423-431 / 466-469): the reference re-evaluates the distances to ALL candidates every
+// round; min_j d(x, c_j) over a growing set is the running minimum of the per-round minima.  This kernel folds the
+// minima of the new candidates into the running minimum and sums the result (the cost phi) in one pass, with a fixed
+// reduction order (per-CTA partial -> last CTA adds them in CTA order), so phi is reproducible.
+// ---------------------------------------------------------------------------------------
+static const int kFoldSlots = 32;
+__device__ double g_fold_part[kFoldSlots][1024];
+__device__ unsigned int g_fold_done[kFoldSlots];
+static std::atomic<unsigned int> g_fold_seq{0};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+min_fold_kernel(T* __restrict__ run_min, const T* __restrict__ new_min, long long n, double* phi_acc, int slot) {
+  __shared__ double sm[8];
+  __shared__ bool last;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    T v = run_min[i];
+    if (new_min) { const T w = new_min[i]; v = w < v ? w : v; run_min[i] = v; }
+    acc += (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += sm[w];
+    g_fold_part[slot][blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(&g_fold_done[slot], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += *(volatile double*)&g_fold_part[slot][b];
+    if (phi_acc) *phi_acc += s;
+    g_fold_done[slot] = 0;
+  }
+}
+
+int launch_min_fold(void* run_min, const void* new_min, long long n, int dtype, double* phi_acc, int sm_count, cudaStream_t s) {
+  if (n == 0) return 0;
+  long long nb = (n + 2047) / 2048;
+  if (nb > 1024) nb = 1024;
+  if (nb > (long long)sm_count * 4) nb = (long long)sm_count * 4;
+  const int slot = (int)(g_fold_seq.fetch_add(1u) % kFoldSlots);
+  if (dtype == BKM_F64) min_fold_kernel<double><<<(int)nb, 256, 0, s>>>((double*)run_min, (const double*)new_min, n, phi_acc, slot);
+  else min_fold_kernel<float><<<(int)nb, 256, 0, s>>>((float*)run_min, (const float*)new_min, n, phi_acc, slot);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Device generator for datasets.make_blobs blocks (dask_ml/datasets.py:178-189: every block is generated on its own
+// from (centres, cluster_std, seed = block index)).  Row i of the block: label = floor(U_i * k) from one Philox stream,
+// features = centre[label] + std[label] * N(0, 1) with Box-Muller normals from a second Philox stream keyed by the same
+// seed; counters are (row, feature pair), so a block is reproducible whatever GPU / grid generates it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_two_words(uint64_t seed, uint64_t ctr, uint32_t& w0, uint32_t& w1) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  w0 = c0; w1 = c1;
+}
+
+template <typename T>
+__global__ void make_blobs_kernel(T* __restrict__ X, long long* __restrict__ y, long long n, int d, long long ldx,
+                                  const double* __restrict__ centers, const double* __restrict__ stds, int k,
+                                  uint64_t seed) {
+  const int pairs = (d + 1) / 2;
+  const long long total = n * pairs;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / pairs;
+    const int p = (int)(e - row * pairs);
+    const uint32_t lw = philox_first_word(seed ^ 0x5bd1e995a5a5a5a5ull, (uint64_t)row);
+    int lab = (int)(((unsigned long long)lw * (unsigned long long)k) >> 32);
+    if (lab >= k) lab = k - 1;
+    uint32_t w0, w1;
+    philox_two_words(seed, (uint64_t)e, w0, w1);
+    const double u1 = ((double)w0 + 1.0) * (1.0 / 4294967296.0);          // (0, 1]
+    const double u2 = (double)w1 * (1.0 / 4294967296.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    const double sd = stds[lab];
+    const int f0 = 2 * p, f1 = 2 * p + 1;
+    X[row * ldx + f0] = (T)(centers[(size_t)lab * d + f0] + sd * rad * cs);
+    if (f1 < d) X[row * ldx + f1] = (T)(centers[(size_t)lab * d + f1] + sd * rad * sn);
+    if (p == 0 && y) y[row] = lab;
+  }
+}
+
+int launch_make_blobs(void* X, long long* y, long long n, int d, long long ldx, int dtype, const double* centers,
+                      const double* stds, int k, uint64_t seed, int sm_count, cudaStream_t s) {
+  if (n == 0) return 0;
+  long long nb = (n * ((d + 1) / 2) + 255) / 256; if (nb > (long long)sm_count * 16) nb = (long long)sm_count * 16;
+  if (dtype == BKM_F32) make_blobs_kernel<float><<<(int)nb, 256, 0, s>>>((float*)X, y, n, d, ldx, centers, stds, k, seed);
+  else make_blobs_kernel<double><<<(int)nb, 256, 0, s>>>((double*)X, y, n, d, ldx, centers, stds, k, seed);
+  note_launch();
+  BKM_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // NaN / inf scan (k_means.py:179-180)
 // ---------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ double cf_to_double(T v) { return (double)v; }

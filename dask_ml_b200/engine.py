@@ -249,6 +249,13 @@ class CudaBackend(object):
                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(row_offset), self._ptr(picked), picked.numel(),
                 self._ptr(n_picked), self._stream()), "bkm_sample_chunk")
 
+    def min_fold(self, run_min, new_min, phi_acc):
+        """run_min = min(run_min, new_min) (new_min may be None) and phi_acc += sum(run_min): one kernel."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bkm_min_fold_chunk(self._ptr(run_min), self._ptr(new_min), run_min.numel(),
+                                                   _DT_CODE[run_min.dtype], self._ptr(phi_acc), self._stream()),
+                       "bkm_min_fold_chunk")
+
     def transform_chunk(self, x, pack, k, out, mode=0, gamma=0.0):
         """(n, k) block of distances (mode 0), squared distances (1) or exp(-gamma d^2) (2) into ``out`` — which may be a
         column block of a wider matrix (row pitch = out.stride(0))."""
@@ -267,21 +274,100 @@ class CudaBackend(object):
                        "bkm_finalize")
 
 
+class StreamedChunks(object):
+    """Row chunks that stay in HOST memory and pass through two device buffers every time they are iterated: the
+    out-of-core ingestion path (data larger than HBM, or simply not uploaded).  Iterating yields device tensors in
+    order; block i+1 is copied host->device on a copy stream while the kernels enqueued for block i run, so X crosses
+    PCIe once per sweep.  A yielded tensor is valid until the iterator is advanced (its buffer is then recycled)."""
+
+    def __init__(self, host_blocks, backend, dtype, block_rows=1 << 20):
+        self.backend = backend
+        self.dtype = dtype
+        self.parts = []                            # (host tensor view of <= block_rows rows)
+        for b in host_blocks:
+            t = b if _is_torch(b) else torch.from_numpy(np.ascontiguousarray(b))
+            t = t.to(dtype) if t.dtype != dtype else t
+            if not t.is_contiguous():
+                t = t.contiguous()
+            if backend.device.type == "cuda" and not t.is_pinned() and t.numel() > 0:
+                # page-lock in place (no second host copy): asynchronous H2D copies need pinned memory
+                try:
+                    rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+                    self._registered = getattr(self, "_registered", []) + ([t] if int(rc) == 0 else [])
+                except Exception:
+                    pass
+            for s0 in range(0, max(1, int(t.shape[0])), block_rows):
+                self.parts.append(t[s0:s0 + block_rows])
+        self.sizes = [int(p.shape[0]) for p in self.parts]
+        self.d = int(self.parts[0].shape[1])
+        self._bufs = None
+
+    def __len__(self):
+        return len(self.parts)
+
+    def __iter__(self):
+        be = self.backend
+        if be.device.type != "cuda":
+            for p in self.parts:
+                yield p
+            return
+        if self._bufs is None:
+            rows = max(self.sizes) if self.sizes else 1
+            pitch = self.d
+            if self.dtype == torch.float32 and self.d % 4 and self.d <= 64:
+                pitch = (self.d + 3) // 4 * 4          # 16-byte rows for the tensor path (see CudaBackend.to_device)
+            if self.dtype == torch.bfloat16 and self.d % 8:
+                pitch = (self.d + 7) // 8 * 8
+            self._bufs = [torch.zeros((max(1, rows), pitch), dtype=self.dtype, device=be.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=be.device)
+        main = torch.cuda.current_stream(be.device)
+        consumed = [None, None]
+        for i, p in enumerate(self.parts):
+            slot = i & 1
+            m = int(p.shape[0])
+            with torch.cuda.stream(self._copy_stream):
+                if consumed[slot] is not None:
+                    self._copy_stream.wait_event(consumed[slot])
+                else:
+                    self._copy_stream.wait_stream(main)       # a previous sweep may still read this buffer
+                self._bufs[slot][:m, :self.d].copy_(p, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            main.wait_event(ev)
+            yield self._bufs[slot][:m, :self.d]
+            done = torch.cuda.Event()
+            done.record(main)
+            consumed[slot] = done
+
+    def __getitem__(self, i):
+        raise TypeError("streamed chunks cannot be indexed; iterate them")
+
+
 class DeviceData(object):
-    """Row chunks of X resident on one device + their place in the global (all-rank) row order."""
+    """Row chunks of X + their place in the global (all-rank) row order.  The chunks are resident on the device
+    (list of tensors) or, for ``HostData``, streamed from host memory on every sweep (``StreamedChunks``)."""
 
     def __init__(self, chunks, backend, comm=None):
-        self.chunks = chunks                      # list of 2-D torch tensors on backend.device
+        self.chunks = chunks                      # list of 2-D torch tensors on backend.device (or StreamedChunks)
         self.backend = backend
         self.comm = comm or Comm()
-        self.dtype = chunks[0].dtype
-        self.d = int(chunks[0].shape[1])
-        self.n_local = int(sum(int(c.shape[0]) for c in chunks))
+        if isinstance(chunks, StreamedChunks):
+            self.dtype, self.d = chunks.dtype, chunks.d
+            self.chunk_rows = list(chunks.sizes)
+        else:
+            self.dtype = chunks[0].dtype
+            self.d = int(chunks[0].shape[1])
+            self.chunk_rows = [int(c.shape[0]) for c in chunks]
+        self._init_layout()
+
+    def _init_layout(self):
+        chunks = self.chunks
+        self.n_local = int(sum(self.chunk_rows))
         sizes = self.comm.allgather_obj(self.n_local)
         self.rank_sizes = [int(s) for s in sizes]
         self.row_offset = int(sum(self.rank_sizes[: self.comm.rank]))
         self.n_global = int(sum(self.rank_sizes))
-        self.chunk_offsets = np.cumsum([0] + [int(c.shape[0]) for c in chunks])
+        self.chunk_offsets = np.cumsum([0] + list(self.chunk_rows))
 
     @property
     def np_dtype(self):
@@ -296,6 +382,14 @@ class DeviceData(object):
         """Rows by LOCAL index -> numpy (len, d)."""
         local_idx = np.asarray(local_idx, dtype=np.int64)
         out = np.empty((len(local_idx), self.d), dtype=self.np_dtype)
+        if isinstance(self.chunks, StreamedChunks):
+            which = np.searchsorted(self.chunk_offsets, local_idx, side="right") - 1
+            for w in np.unique(which):
+                pos = np.nonzero(which == w)[0]
+                part = self.chunks.parts[w]
+                sel = part[torch.as_tensor(local_idx[pos] - self.chunk_offsets[w], dtype=torch.int64)]
+                out[pos] = (sel.float() if sel.dtype == torch.bfloat16 else sel).numpy()
+            return out
         which = np.searchsorted(self.chunk_offsets, local_idx, side="right") - 1
         # one gather + one device-to-host copy per chunk that holds requested rows (not one copy per row)
         for w in np.unique(which):
@@ -321,4 +415,22 @@ class DeviceData(object):
 
     def to_host(self):
         """All LOCAL rows as one numpy array (used only by the in-memory k-means++ init)."""
-        return np.concatenate([(c.float() if c.dtype == torch.bfloat16 else c).cpu().numpy() for c in self.chunks], axis=0)
+        src = self.chunks.parts if isinstance(self.chunks, StreamedChunks) else self.chunks
+        return np.concatenate([(c.float() if c.dtype == torch.bfloat16 else c).cpu().numpy() for c in src], axis=0)
+
+
+def host_resident(X, backend=None, comm=None, block_rows=1 << 20):
+    """Wrap host-resident data (ndarray / CPU tensor / ChunkedArray of host blocks) for OUT-OF-CORE use: ``KMeans.fit``,
+    ``predict`` and the metrics then stream the rows through two device buffers on every sweep instead of uploading X
+    (``StreamedChunks``).  Use it for data larger than HBM; everything else is unchanged (same kernels, same results)."""
+    from .chunked import ChunkedArray as _CA
+
+    backend = backend or CudaBackend()
+    blocks = X.blocks if isinstance(X, _CA) else [X]
+    first = blocks[0]
+    if _is_torch(first):
+        dt = first.dtype if first.dtype in (torch.float32, torch.float64, torch.bfloat16) else torch.float64
+    else:
+        nd = np.dtype(first.dtype)
+        dt = torch.float32 if nd in (np.dtype("float32"), np.dtype("int32"), np.dtype("float16")) else torch.float64
+    return DeviceData(StreamedChunks(blocks, backend, dt, block_rows), backend, comm)

@@ -65,7 +65,7 @@ def _distance_blocks(X, Y, mode, gamma=0.0):
     Y64 = np.ascontiguousarray(Y, dtype=np.float64)
     k = int(Y64.shape[0])
     step = 256
-    outs = [be.empty((int(x.shape[0]), k), X.dtype) for x in X.chunks]
+    outs = [be.empty((m, k), X.dtype) for m in X.chunk_rows]
     for c0 in range(0, k, step):
         c1 = min(k, c0 + step)
         C = torch.as_tensor(Y64[c0:c1]).to(be.device)

@@ -126,6 +126,12 @@ int bkm_sample_chunk(const void* min_d2, int64_t n, int x_dtype,
                      double ell_over_phi, uint64_t seed, uint64_t row_offset,
                      int64_t* picked, int64_t cap, int* n_picked, void* stream);
 
+/* ---- k-means|| running minimum + cost (k_means.py:423-431, 466-469) ---------------------------------------------
+ * run_min[i] = min(run_min[i], new_min[i]) (new_min nullable: cost only) and *phi_acc += sum_i run_min[i], in one
+ * pass with a fixed reduction order.  min_d2 vectors have the dtype bkm_assign_chunk wrote them in (float32 for
+ * float32 / bfloat16 rows, float64 for float64 rows): pass that as x_dtype. */
+int bkm_min_fold_chunk(void* run_min, const void* new_min, int64_t n, int x_dtype, double* phi_acc, void* stream);
+
 /* ---- transform: full (n,k) block of distances / kernel values -------------------------------------------------
  * replaces per chunk: metrics.euclidean_distances(X, Y[, squared])  pairwise.py:69-97  (KMeans.transform k_means.py:207-210)
  *                     metrics.rbf_kernel(X, Y, gamma) = exp(-gamma * d^2)  pairwise.py:131-139
@@ -160,6 +166,15 @@ int bkm_loop_state_bytes(size_t* out);
 int bkm_loop_reset(void* loop_state, double tol, double* shift_hist, int hist_cap, void* stream);
 int bkm_finalize_step(const double* reduced, const double* centers_in, double* centers_out, void* loop_state,
                       int k, int d, int x_dtype, void* pack, size_t pack_bytes, void* stream);
+
+/* ---- datasets.make_blobs, one block on the device (dask_ml/datasets.py:178-189) ---------------------------------
+ * The reference generates every block independently from (centres, cluster_std, seed = block index) with
+ * sklearn.datasets.make_blobs; this is the device-side equivalent of ONE block: label_i ~ U{0..k-1}, row_i =
+ * centres[label_i] + cluster_std[label_i] * N(0, I), Philox4x32-10 streams keyed by `seed` with (row, feature pair)
+ * counters (reproducible per block whatever GPU generates it; numpy's Mersenne-Twister stream is not reproduced).
+ * X [n][ldx] x-dtype out, y [n] int64 out (nullable); centers [k][d] and cluster_std [k] float64 on the device. */
+int bkm_make_blobs_chunk(void* X, int64_t* y, int64_t n, int d, int64_t ldx, int x_dtype, const double* centers,
+                         const double* cluster_std, int k, uint64_t seed, void* stream);
 
 /* ---- NaN/inf scan of a chunk (k_means.py:179-180): sets *flag (int32) nonzero -------- */
 int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,

@@ -79,8 +79,16 @@ class OracleBackend(object):
             picked[base:base + m] = torch.from_numpy(hit[:m].astype(np.int64))
         n_picked += len(hit)
 
-    def transform_chunk(self, x, pack, k, out):
-        d = ok.euclidean_distances([x.numpy()], pack.numpy().astype(x.numpy().dtype))[0]
+    def min_fold(self, run_min, new_min, phi_acc):
+        if new_min is not None:
+            torch.minimum(run_min, new_min, out=run_min)
+        if phi_acc is not None:
+            phi_acc += run_min.sum(dtype=torch.float64)
+
+    def transform_chunk(self, x, pack, k, out, mode=0, gamma=0.0):
+        d = ok.euclidean_distances([x.numpy()], pack.numpy().astype(x.numpy().dtype), squared=mode != 0)[0]
+        if mode == 2:
+            d = np.exp(-gamma * d)
         out.copy_(torch.from_numpy(d).to(out.dtype))
 
     def finalize(self, sums, counts, C_old, C_new, shift):

@@ -247,3 +247,115 @@ def test_engine_matches_fixtures_written_by_the_reference(name):
     tr = km.transform(X).compute()[:256]
     scale = np.sqrt((g["X"][:256].astype(np.float64) ** 2).sum(1)[:, None] + (g["centers"].astype(np.float64) ** 2).sum(1)[None])
     assert np.max(np.abs(tr - g["transform"]) / scale) < (2e-3 if g["X"].dtype == np.float32 else 1e-9)
+
+
+def test_make_blobs_device_generator_and_c1_through_the_package(oracle):
+    """BASELINE config C1 through the package: datasets.make_blobs (100k x 16 float64, 8 blocks, k = 8) -> KMeans.fit,
+    against the oracle on the same blocks; plus the device generator's per-block seeding contract."""
+    import torch
+    from dask_ml_b200.cluster import KMeans
+    from dask_ml_b200.datasets import make_blobs
+
+    X, y = make_blobs(n_samples=100_000, n_features=16, centers=8, random_state=0, chunks=12_500)
+    init = X.blocks[0][:8].copy()
+    km = KMeans(8, init=init, max_iter=20).fit(X)
+    lab, inertia, C, n_iter = oracle.kmeans_single_lloyd([np.asarray(b) for b in X.blocks], 8, init=init, max_iter=20)
+    assert km.n_iter_ == n_iter
+    assert int((km.labels_.compute() != np.concatenate(lab)).sum()) == 0
+    assert abs(km.inertia_ - inertia) <= 1e-9 * inertia
+    # device generator: blocks live on the GPU, block i depends on (centres, i) only
+    Xd, yd = make_blobs(n_samples=40_000, n_features=16, centers=8, random_state=0, chunks=10_000, device="cuda")
+    Xe, ye = make_blobs(n_samples=25_000, n_features=16, centers=8, random_state=0, chunks=10_000, device="cuda")
+    assert Xd.blocks[0].is_cuda and Xd.dtype == np.float64 and yd.dtype == np.int64
+    assert torch.equal(Xd.blocks[1], Xe.blocks[1]) and torch.equal(yd.blocks[1], ye.blocks[1])
+    assert not torch.equal(Xd.blocks[0], Xd.blocks[1])
+    Xh, yh = Xd.compute(), yd.compute()
+    Xp, yp = make_blobs(n_samples=10_000, n_features=16, centers=8, random_state=0, chunks=10_000)    # same prototype
+    for c in range(8):
+        assert abs((yh == c).mean() - 0.125) < 0.01
+        np.testing.assert_allclose(Xh[yh == c].mean(0), Xp.compute()[yp.compute() == c].mean(0), atol=0.1)
+        assert abs(Xh[yh == c].std(0).mean() - 1.0) < 0.02
+    X32, _ = make_blobs(n_samples=1000, n_features=5, centers=3, random_state=1, chunks=500, device="cuda", dtype="float32")
+    assert X32.dtype == np.float32
+    KMeans(3, init="k-means||", random_state=0).fit(X32)
+
+
+def test_kmeans_parallel_candidates_match_oracle_with_the_same_philox_stream(oracle):
+    """k-means|| steps 1-6 on the GPU against the oracle's restatement of k_means.py:396-435 driven by the SAME
+    Philox draws (the reference's own dask draws cannot be reproduced: sampling parity is pinned to this stream):
+    identical candidate sets, hence identical cost phi after every round."""
+    import torch
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import k_means as km
+
+    rng = np.random.RandomState(4)
+    cent = rng.uniform(-15, 15, size=(12, 10))
+    X = (cent[rng.randint(0, 12, size=60_000)] + rng.standard_normal((60_000, 10))).astype(np.float32)
+    ell = 12
+    Xd = km._to_device_data(ChunkedArray.from_array(X, 17_000))
+    rs = np.random.RandomState(11)
+    got = km._scalable_candidates(Xd, rs, None, ell)
+    # the oracle's loop with the engine's per-round seeds
+    rs2 = np.random.RandomState(11)
+    blocks = oracle.to_blocks(X, 17_000)
+    c_idx = {0}
+    cost = oracle.evaluate_cost(blocks, oracle._rows(blocks, [0]))
+    n_iter = int(np.round(np.log(cost)))
+    for _ in range(n_iter):
+        seed = int(rs2.randint(0, 2 ** 31 - 1)) | (int(rs2.randint(0, 2 ** 31 - 1)) << 32)
+        draw = lambda off, n, seed=seed: oracle.philox_uniform(seed, np.arange(n, dtype=np.uint64) + np.uint64(off))
+        c_idx |= set(oracle.sample_points(blocks, oracle._rows(blocks, sorted(c_idx)), ell, draw))
+    want = sorted(c_idx)
+    # float32 distances vs the oracle's float64: a draw within rounding of its threshold may flip
+    assert len(set(got) ^ set(want)) <= max(2, len(want) // 100), (len(got), len(want))
+    phi_got = km.evaluate_cost(Xd, Xd.global_rows(got))
+    phi_want = oracle.evaluate_cost(blocks, oracle._rows(blocks, want))
+    assert abs(phi_got - phi_want) <= 0.02 * phi_want
+
+
+def test_gpu_candidate_reduce_unweighted_and_weighted():
+    """Steps 7-8 on the GPU: the reduced init must be about as good as scikit-learn's KMeans on the same candidates
+    (what the reference runs, k_means.py:457-463), and the weighted variant at least as good in cost over X."""
+    from sklearn.cluster import KMeans as SK
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import k_means as km
+
+    rng = np.random.RandomState(9)
+    cent = rng.uniform(-20, 20, size=(15, 6))
+    X = (cent[rng.randint(0, 15, size=40_000)] + 0.5 * rng.standard_normal((40_000, 6))).astype(np.float32)
+    Xd = km._to_device_data(ChunkedArray.from_array(X, 10_000))
+    cand_idx = km._scalable_candidates(Xd, np.random.RandomState(0), None, 30)
+    cand = Xd.global_rows(cand_idx)
+    assert len(cand) > 15
+    a = km._reduce_candidates(cand, 15, 123, Xd.backend)
+    b = SK(15, random_state=0, n_init=10).fit(cand).cluster_centers_
+    ca, cb = km.evaluate_cost(Xd, a), km.evaluate_cost(Xd, b)
+    assert ca <= 1.25 * cb, (ca, cb)
+    c_unw = km.k_init(Xd, 15, "k-means||", random_state=2, oversampling_factor=30)
+    c_w = km.k_init(Xd, 15, "k-means||", random_state=2, oversampling_factor=30, weighted=True)
+    assert c_unw.shape == c_w.shape == (15, 6)
+    assert km.evaluate_cost(Xd, c_w) <= 1.5 * km.evaluate_cost(Xd, c_unw)
+
+
+def test_host_resident_streaming_on_the_gpu(oracle):
+    """Out-of-core ingestion: X stays in (pinned) host memory and is streamed through two device buffers on every sweep;
+    same labels / centres as the resident fit and as the oracle."""
+    import torch
+    from dask_ml_b200.cluster import KMeans
+    from dask_ml_b200.engine import host_resident
+
+    rng = np.random.RandomState(8)
+    cent = rng.uniform(-10, 10, size=(30, 41))
+    X = (cent[rng.randint(0, 30, size=50_000)] + rng.standard_normal((50_000, 41))).astype(np.float32)
+    init = X[:100].copy()
+    a = KMeans(100, init=init, max_iter=6, tol=0.0).fit(X)
+    Xh = host_resident(X, block_rows=12_000)
+    assert not isinstance(Xh.chunks, list) and len(Xh.chunks) == 5
+    b = KMeans(100, init=init, max_iter=6, tol=0.0).fit(Xh)
+    assert a.n_iter_ == b.n_iter_ == 6
+    assert int((a.labels_.compute() != b.labels_.compute()).sum()) == 0
+    np.testing.assert_allclose(a.cluster_centers_, b.cluster_centers_, rtol=1e-6, atol=1e-6)
+    assert abs(a.inertia_ - b.inertia_) <= 1e-9 * a.inertia_
+    assert int((b.predict(Xh).compute() != a.predict(X).compute()).sum()) == 0
+    tr = b.transform(Xh).compute()
+    np.testing.assert_allclose(tr, a.transform(X).compute(), rtol=1e-5, atol=1e-4)

@@ -212,3 +212,55 @@ def test_kmeans_parallel_init_is_chunking_invariant(cpu_engine, oracle):
     b = km_mod.k_init(ChunkedArray.from_array(X, 700), 6, "k-means||", random_state=5, oversampling_factor=8)
     np.testing.assert_allclose(a, b, rtol=1e-12)
     assert a.shape == (6, 5)
+
+
+# ------------------------------------------------------------------------------------------ datasets.make_blobs
+def test_make_blobs_host_path_is_the_reference_contract(oracle):
+    """datasets.py:154-202: prototype centres from one scikit-learn call with the user seed, block i from
+    sklearn.make_blobs(random_state=i).  The product's host path must equal the oracle's restatement bit for bit."""
+    import sklearn.datasets
+    from dask_ml_b200.datasets import make_blobs
+
+    X, y = make_blobs(n_samples=1000, n_features=16, centers=8, random_state=0, chunks=125)
+    Xo, yo = oracle.make_blobs(n_samples=1000, n_features=16, centers=8, random_state=0, chunks=125)
+    assert X.chunks == ((125,) * 8, (16,)) and y.chunks == ((125,) * 8,)
+    assert X.dtype == np.float64 and y.dtype == np.int64
+    for a, b in zip(X.blocks, Xo):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(y.blocks, yo):
+        np.testing.assert_array_equal(a, b)
+    # block 3 is sklearn's block with random_state=3 around the same prototype centres
+    Xp, yp = sklearn.datasets.make_blobs(n_samples=125, n_features=16, centers=8, random_state=0)
+    proto = np.stack([Xp[yp == i].mean(0) for i in range(8)])
+    X3, _ = sklearn.datasets.make_blobs(n_samples=125, n_features=16, centers=proto, random_state=3)
+    np.testing.assert_array_equal(X.blocks[3], X3)
+    # explicit centres, ragged last block, blockshape form
+    C = np.array([[0.0, 0.0], [5.0, 5.0]])
+    X2, y2 = make_blobs(n_samples=250, n_features=2, centers=C, cluster_std=0.1, chunks=(100, 2), random_state=1)
+    assert X2.chunks[0] == (100, 100, 50)
+    assert np.abs(X2.compute()[y2.compute() == 1].mean(0) - 5.0).max() < 0.1
+    with pytest.raises(ValueError):
+        make_blobs(n_samples=100, n_features=4, chunks=(50, 2))
+
+
+def test_host_resident_streaming_gives_the_same_fit(cpu_engine, oracle):
+    """Out-of-core path: rows that stay in host memory and are streamed block by block on every sweep must give exactly
+    the fit of the resident path (same kernels in the same order; here through the CPU checker backend)."""
+    from oracle_backend import OracleBackend
+    from dask_ml_b200.cluster import KMeans
+    from dask_ml_b200.engine import host_resident
+
+    rng = np.random.RandomState(5)
+    X = (rng.uniform(-5, 5, size=(4, 6))[rng.randint(0, 4, size=3000)] + rng.standard_normal((3000, 6))).astype(np.float32)
+    init = X[:4].copy()
+    a = KMeans(4, init=init, max_iter=10).fit(X)
+    Xh = host_resident(X, backend=OracleBackend(), block_rows=700)       # 5 streamed blocks
+    assert Xh.chunk_rows == [700, 700, 700, 700, 200] and Xh.n_local == 3000
+    b = KMeans(4, init=init, max_iter=10).fit(Xh)
+    assert a.n_iter_ == b.n_iter_
+    np.testing.assert_array_equal(a.labels_.compute(), b.labels_.compute())
+    np.testing.assert_allclose(a.cluster_centers_, b.cluster_centers_, rtol=1e-12)
+    np.testing.assert_array_equal(b.predict(Xh).compute(), a.predict(X).compute())
+    c = KMeans(4, init="k-means||", random_state=0, oversampling_factor=6, max_iter=5).fit(Xh)
+    d = KMeans(4, init="k-means||", random_state=0, oversampling_factor=6, max_iter=5).fit(X)
+    np.testing.assert_allclose(c.cluster_centers_, d.cluster_centers_, rtol=1e-9)
