@@ -342,7 +342,7 @@ stream_chunk_kernel(ChunkArgs a, StreamSmem S) {
 static const int S2_NSTG = 3;       // ring stages per warp (64 rows each)
 
 struct Stream2Smem {
-  uint32_t off_c, off_cn, off_sums, off_cnt, off_red, off_bar, off_slot, off_ring, stage_bytes, total;
+  uint32_t off_c, off_cn, off_cnt, off_red, off_bar, off_slot, off_lab, off_wsum, off_ring, stage_bytes, total;
 };
 static inline Stream2Smem stream2_smem(int k, int d, long long ldx, int kc, int dp) {
   Stream2Smem S;
@@ -350,18 +350,42 @@ static inline Stream2Smem stream2_smem(int k, int d, long long ldx, int kc, int 
   S.off_c = o;    o += (uint32_t)kc * dp * 4;             // [kc][dp] floats: -2 c (zero padded)
   S.off_cn = o;   o += (uint32_t)kc * 4;                  // [kc] ||c||^2 (+inf for j >= k)
   o = (uint32_t)align_up(o, 16);
-  S.off_sums = o; o += (uint32_t)k * d * 4;
-  o = (uint32_t)align_up(o, 16);
   S.off_cnt = o;  o += (uint32_t)k * 4;
   o = (uint32_t)align_up(o, 16);
   S.off_red = o;  o += SW * 8;
   S.off_bar = o;  o += SW * S2_NSTG * 8;
   S.off_slot = o; o += SW * 64 * 4;                       // per warp: two row masks per cluster
+  S.off_lab = o;  o += SW * 64 * 4;                       // per warp: the tile's labels (invalid rows -> kc, a trash slot)
+  o = (uint32_t)align_up(o, 128);
+  S.off_wsum = o; o += (uint32_t)SW * (kc + 1) * 32 * 4;  // per warp: [kc + 1][2 row halves][16 features] running sums
   o = (uint32_t)align_up(o, 128);
   S.stage_bytes = (uint32_t)(64 * ldx * 4);
   S.off_ring = o; o += (uint32_t)SW * S2_NSTG * S.stage_bytes + 128;      // + slack: the M-step reads whole DP-float rows
   S.total = o;
   return S;
+}
+
+// M-step of one 64-row tile: lane (f = lane & 15, h = lane >> 4) adds feature f of 32 rows into the warp's private
+// shared-memory sums [label][h][f] (plain load / add / store: each address belongs to one lane, and the two halves of
+// the warp have their own copies, so there is no race and the order is fixed).  The trip count does not depend on how
+// the rows are spread over the clusters (the lane-owns-cluster walk ran for the LONGEST list of the tile: 12 of 64
+// rows on the airline-shaped data).  Half h takes rows r0(i) + h * S, S chosen from the row pitch so that the two
+// halves read different banks (S * L = 16 mod 32 when L has fewer than 5 trailing zero bits).
+template <int S>
+__device__ __forceinline__ void stream2_mstep_tile(const float* xs_lane, const int* lab_h, float* ws, int L) {
+#pragma unroll
+  for (int b = 0; b < 32; b += 8) {
+    int l[8];
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r0 = (((b + i) & ~(S - 1)) << 1) + ((b + i) & (S - 1));
+      l[i] = lab_h[r0];
+      x[i] = xs_lane[r0 * L];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ws[l[i] * 32] += x[i];
+  }
 }
 
 // DH = feature pairs (DP = 2 DH >= d), KC = centres rounded up to a multiple of 4 (<= 24)
@@ -378,7 +402,6 @@ stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
   const int L = (int)a.ldx;
   float* cs = reinterpret_cast<float*>(smem + S.off_c);
   float* cns = reinterpret_cast<float*>(smem + S.off_cn);
-  float* sums_s = reinterpret_cast<float*>(smem + S.off_sums);
   int* cnts_s = reinterpret_cast<int*>(smem + S.off_cnt);
   double* red_s = reinterpret_cast<double*>(smem + S.off_red);
   const float* gC = reinterpret_cast<const float*>(a.pack + a.L.off_cT);      // [k][d4] fp32, zero padded
@@ -394,9 +417,10 @@ stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
     cs[i] = (j < k && f < d) ? -2.f * gC[(size_t)j * d4 + f] : 0.f;
   }
   for (int j = tid; j < KC; j += SW * 32) cns[j] = j < k ? gCn[j] : CUDART_INF_F;
+  float* wsum = reinterpret_cast<float*>(smem + S.off_wsum);               // [SW][KC + 1][2][16]
   if (MSTEP) {
-    for (int i = tid; i < k * d; i += SW * 32) sums_s[i] = 0.f;
     for (int i = tid; i < k; i += SW * 32) cnts_s[i] = 0;
+    for (int i = tid; i < SW * (KC + 1) * 32; i += SW * 32) wsum[i] = 0.f;
   }
   const float cnmax = (float)hdr->cn_max;
 
@@ -423,10 +447,13 @@ stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
     }
   }
 
-  float macc[MSTEP ? DP : 1];
-#pragma unroll
-  for (int i = 0; i < (MSTEP ? DP : 1); ++i) macc[i] = 0.f;
   int mcnt = 0;
+  // pairing of the two half-warps' rows (see stream2_mstep_tile)
+  const int tzL = __ffs(L) - 1;
+  const int msS = tzL >= 4 ? 1 : (16 >> tzL);
+  const int mf = lane & 15, mh = lane >> 4;
+  int* lab_w = reinterpret_cast<int*>(smem + S.off_lab) + warp * 64;
+  float* ws_lane = wsum + (size_t)warp * (KC + 1) * 32 + mh * 16 + mf;
   double dsum = 0.0;
   const bool want_dist = a.want_sum || a.min_out != nullptr;
 
@@ -584,40 +611,27 @@ stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
       }
     }
 
-    // ---- M-step: lane j takes the rows of this 64-row tile labelled j ----
+    // ---- M-step: counts per cluster from the label masks, sums through the per-warp shared-memory accumulators ----
     if (MSTEP) {
       unsigned* slot = reinterpret_cast<unsigned*>(smem + S.off_slot) + warp * 64;
       slot[lane] = 0u; slot[32 + lane] = 0u;
+      lab_w[lane] = bjr[0] >= 0 ? bjr[0] : KC;
+      lab_w[32 + lane] = bjr[1] >= 0 ? bjr[1] : KC;
       const unsigned same0 = __match_any_sync(0xffffffffu, bjr[0]);
       const unsigned same1 = __match_any_sync(0xffffffffu, bjr[1]);
       __syncwarp();
       if (bjr[0] >= 0) slot[bjr[0]] = same0;
       if (bjr[1] >= 0) slot[32 + bjr[1]] = same1;
       __syncwarp();
-      unsigned mine0 = slot[lane], mine1 = slot[32 + lane];
-      mcnt += __popc(mine0) + __popc(mine1);
-#pragma unroll 1
-      while (__any_sync(0xffffffffu, (mine0 | mine1) != 0u)) {
-        if (mine0 | mine1) {
-          int b;
-          if (mine0) { b = __ffs(mine0) - 1; mine0 &= mine0 - 1; }
-          else { b = 32 + __ffs(mine1) - 1; mine1 &= mine1 - 1; }
-          const float* xr = xs + b * L;
-          if ((L & 3) == 0) {
-#pragma unroll
-            for (int q = 0; q < D4; ++q) {
-              const float4 v = *reinterpret_cast<const float4*>(xr + q * 4);
-              macc[q * 4 + 0] += v.x;
-              if (q * 4 + 1 < DP) macc[q * 4 + 1] += v.y;
-              if (q * 4 + 2 < DP) macc[q * 4 + 2] += v.z;
-              if (q * 4 + 3 < DP) macc[q * 4 + 3] += v.w;
-            }
-          } else {
-            // whole DP-float rows (the ring has slack behind it): entries >= d are never flushed
-#pragma unroll
-            for (int i = 0; i < (MSTEP ? DP : 1); ++i) macc[i] += xr[i];
-          }
-        }
+      mcnt += __popc(slot[lane]) + __popc(slot[32 + lane]);
+      const float* xl = xs + mh * msS * L + mf;
+      const int* lh = lab_w + mh * msS;
+      switch (msS) {
+        case 16: stream2_mstep_tile<16>(xl, lh, ws_lane, L); break;
+        case 8: stream2_mstep_tile<8>(xl, lh, ws_lane, L); break;
+        case 4: stream2_mstep_tile<4>(xl, lh, ws_lane, L); break;
+        case 2: stream2_mstep_tile<2>(xl, lh, ws_lane, L); break;
+        default: stream2_mstep_tile<1>(xl, lh, ws_lane, L); break;
       }
     }
 
@@ -634,16 +648,21 @@ stream2_chunk_kernel(ChunkArgs a, Stream2Smem S) {
 
   if (MSTEP) {
     for (int w = 0; w < SW; ++w) {
-      if (warp == w && lane < k) {
-#pragma unroll
-        for (int i = 0; i < (MSTEP ? DP : 1); ++i)
-          if (i < d) sums_s[lane * d + i] += macc[i];
-        cnts_s[lane] += mcnt;
-      }
+      if (warp == w && lane < k) cnts_s[lane] += mcnt;
       __syncthreads();
     }
+    // per-CTA partial: the 2 * SW accumulators of (cluster, feature) added in a fixed order
     float* g = reinterpret_cast<float*>(a.psum) + (size_t)blockIdx.x * k * d;
-    for (int i = tid; i < k * d; i += SW * 32) g[i] = sums_s[i];
+    for (int i = tid; i < k * d; i += SW * 32) {
+      const int j = i / d, f = i - j * d;
+      float sacc = 0.f;
+      for (int w = 0; w < SW; ++w) {
+        const float* p = wsum + ((size_t)w * (KC + 1) + j) * 32 + f;
+        sacc += p[0];
+        sacc += p[16];
+      }
+      g[i] = sacc;
+    }
     int* gc = a.pcnt + (size_t)blockIdx.x * k;
     for (int i = tid; i < k; i += SW * 32) gc[i] = cnts_s[i];
   }
