@@ -53,6 +53,7 @@ SIGNATURES = {
     "bkm_finalize": (_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _int, _int, _c_void_p]),
     "bkm_check_finite": (_int, [_c_void_p, _i64, _int, _i64, _int, _c_void_p, _c_void_p]),
     "bkm_launch_count": (_i64, []),
+    "bkm_debug_fallback_count": (_i64, []),
     "bkm_debug_abort_code": (ctypes.c_uint, []),
     "bkm_debug_abort_detail": (None, [_c_void_p]),
     "bkm_debug_trace": (_int, [_c_void_p, _int]),

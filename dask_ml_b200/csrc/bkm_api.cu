@@ -44,6 +44,8 @@ static int sm_count_of_current(int* out) {
 // sum|x_i c_i| <= (||x||^2+||c||^2)/2; both distances and the -2 factor give the constant.
 static bool dtype_ok(int x_dtype) { return x_dtype == BKM_F32 || x_dtype == BKM_F64 || x_dtype == BKM_BF16; }
 
+static std::atomic<long long> g_fallbacks{0};   // chunk calls that left their shape's kernel family for the generic kernel
+
 static float tau_for(int d, int dtype, int flags, int family) {
   if (dtype == BKM_F64 || (flags & BKM_FLAG_NO_RECHECK)) return 0.f;
   const float eps = 1.0f / 16777216.0f;   // 2^-24
@@ -118,6 +120,7 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (family == 1) {
     rc = launch_tc(a, mstep, sm, &grid, s);
     if (rc == BKM_EALIGN && !(flags & BKM_FLAG_FORCE_TC)) {   // TMA needs 16-byte aligned rows
+      g_fallbacks.fetch_add(1, std::memory_order_relaxed);
       family = 0;
       a.tau = tau_for(d, x_dtype, flags, 0);
     }
@@ -125,6 +128,7 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   if (family == 2) {
     rc = launch_stream(a, mstep, sm, &grid, s);
     if (rc == BKM_EALIGN || rc == BKM_EUNSUPPORTED) {          // odd base pointer / very wide pitch: generic kernel
+      g_fallbacks.fetch_add(1, std::memory_order_relaxed);
       family = 0;
       a.tau = tau_for(d, x_dtype, flags, 0);
     }
@@ -327,6 +331,7 @@ int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype, 
 }
 
 int64_t bkm_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t bkm_debug_fallback_count(void) { return (int64_t)g_fallbacks.load(); }
 
 unsigned int bkm_debug_abort_code(void) { return bkm::tc_abort_code(); }
 void bkm_debug_abort_detail(unsigned int* out64_host) { bkm::tc_abort_detail(out64_host); }

@@ -750,6 +750,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       }
       int cnt = 0;
       const bool two = KB > 1;
+      const int nq2 = (a.d - 32 + 3) >> 2;          // chunks of the second K-block in use
 #pragma unroll 1
       for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * gridDim.x;
@@ -775,10 +776,13 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
                 acc[q * 4 + 0] += t.x; acc[q * 4 + 1] += t.y; acc[q * 4 + 2] += t.z; acc[q * 4 + 3] += t.w;
               }
               if (two) {
+                // second K-block: only the 16-byte chunks that hold features (d = 41: 3 of 8)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const float4 t = *reinterpret_cast<const float4*>(xr + KBLK_BYTES + ((q ^ sw) << 4));
-                  acc[32 + q * 4 + 0] += t.x; acc[32 + q * 4 + 1] += t.y; acc[32 + q * 4 + 2] += t.z; acc[32 + q * 4 + 3] += t.w;
+                  if (q < nq2) {
+                    const float4 t = *reinterpret_cast<const float4*>(xr + KBLK_BYTES + ((q ^ sw) << 4));
+                    acc[32 + q * 4 + 0] += t.x; acc[32 + q * 4 + 1] += t.y; acc[32 + q * 4 + 2] += t.z; acc[32 + q * 4 + 3] += t.w;
+                  }
                 }
               }
               ++cnt;

@@ -116,6 +116,22 @@ class CudaBackend(object):
     def launch_count(self):
         return int(self.lib.bkm_launch_count())
 
+    _fallbacks_seen = 0
+
+    def _note_fallback(self, x):
+        """Warn (once per process) when a chunk whose shape belongs to the tensor / streaming kernels ran on the generic
+        CUDA-core kernel because its rows are not 16-byte aligned — results are identical, throughput is not."""
+        c = int(self.lib.bkm_debug_fallback_count())
+        if c != CudaBackend._fallbacks_seen:
+            first = CudaBackend._fallbacks_seen == 0
+            CudaBackend._fallbacks_seen = c
+            if first:
+                import warnings
+                warnings.warn("dask_ml_b200: a chunk with shape %s, row pitch %d elements, base address %% 16 = %d is not "
+                              "16-byte aligned; the generic CUDA-core kernel is used instead of the tcgen05 / streaming "
+                              "kernel (pass the data through CudaBackend.to_device, which pads the row pitch)"
+                              % (tuple(x.shape), x.stride(0), x.data_ptr() % 16), RuntimeWarning, stacklevel=3)
+
     def abort_code(self):
         """Non-zero once a pipeline wait of the tensor kernel has timed out (synchronises the device)."""
         return int(self.lib.bkm_debug_abort_code())
@@ -206,6 +222,7 @@ class CudaBackend(object):
                 self._ptr(labels), self._ptr(min_d2), self._ptr(sums), self._ptr(counts),
                 self._ptr(inertia), self._ptr(ws), ws.numel(), flags, self._ptr(loop_state), self._stream()),
                 "bkm_lloyd_chunk")
+        self._note_fallback(x)
 
     # -- device-resident Lloyd loop ------------------------------------------------------
     def loop_state_new(self, tol, max_iter):
@@ -241,6 +258,7 @@ class CudaBackend(object):
                 self._ptr(x), n, d, x.stride(0) if n else d, _DT_CODE[x.dtype], self._ptr(pack), k,
                 self._ptr(labels), self._ptr(min_dist), int(bool(squared)), self._ptr(dist_sum),
                 self._ptr(ws), ws.numel(), self.flags, self._stream()), "bkm_assign_chunk")
+        self._note_fallback(x)
 
     def sample_chunk(self, min_d2, ell_over_phi, seed, row_offset, picked, n_picked):
         with torch.cuda.device(self.device):

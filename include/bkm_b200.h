@@ -182,6 +182,10 @@ int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
 
 /* Number of kernel launches this library has enqueued since load (for bench accounting). */
 int64_t bkm_launch_count(void);
+/* Number of chunk calls whose shape belongs to the tcgen05 / streaming family but whose rows were not 16-byte aligned
+ * (base or pitch), so that the generic CUDA-core kernel ran instead: correct, several times slower.  The Python host
+ * warns once when this moves. */
+int64_t bkm_debug_fallback_count(void);
 
 /* Debug: nonzero once a pipeline wait inside the tcgen05 kernel has timed out (the kernel then drains
  * instead of hanging); encodes barrier / parity / warp.  Synchronises the device. */
