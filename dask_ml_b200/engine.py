@@ -11,6 +11,7 @@ One process drives one GPU.  With ``torch.distributed`` initialised each rank ho
 chunks; without it the engine is single-GPU.
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -292,6 +293,19 @@ class CudaBackend(object):
                        "bkm_finalize")
 
 
+def _host_unregister(tensors):
+    """End the page-lock registrations made by ``StreamedChunks`` (runs when it is collected or at interpreter exit,
+    while the tensors — and so the memory — are still alive)."""
+    try:
+        rt = torch.cuda.cudart()
+        torch.cuda.synchronize()                   # no copy may still read the pages
+        for t in tensors:
+            rt.cudaHostUnregister(t.data_ptr())
+    except Exception:
+        pass
+    del tensors[:]
+
+
 class StreamedChunks(object):
     """Row chunks that stay in HOST memory and pass through two device buffers every time they are iterated: the
     out-of-core ingestion path (data larger than HBM, or simply not uploaded).  Iterating yields device tensors in
@@ -302,18 +316,23 @@ class StreamedChunks(object):
         self.backend = backend
         self.dtype = dtype
         self.parts = []                            # (host tensor view of <= block_rows rows)
+        registered = []                            # host tensors page-locked here (kept alive until unregistered)
+        self._unpin = weakref.finalize(self, _host_unregister, registered)
         for b in host_blocks:
             t = b if _is_torch(b) else torch.from_numpy(np.ascontiguousarray(b))
             t = t.to(dtype) if t.dtype != dtype else t
             if not t.is_contiguous():
                 t = t.contiguous()
             if backend.device.type == "cuda" and not t.is_pinned() and t.numel() > 0:
-                # page-lock in place (no second host copy): asynchronous H2D copies need pinned memory
+                # page-lock in place (no second host copy): asynchronous H2D copies need pinned memory.  The
+                # registration MUST end before the memory is released: a stale registration of a recycled address
+                # range makes later device->host copies of unrelated tensors land in the wrong pages.
                 try:
                     rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
-                    self._registered = getattr(self, "_registered", []) + ([t] if int(rc) == 0 else [])
                 except Exception:
-                    pass
+                    rc = 1
+                if int(rc) == 0:
+                    registered.append(t)
             for s0 in range(0, max(1, int(t.shape[0])), block_rows):
                 self.parts.append(t[s0:s0 + block_rows])
         self.sizes = [int(p.shape[0]) for p in self.parts]
