@@ -344,6 +344,17 @@ def time_lloyd(st, steps, warmup, barrier, world, dev):
     return float(t[0]) / steps, float(t[1]), int(launches)
 
 
+def _static_traffic(name):
+    """DRAM bytes per launch of the config's dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json; not measured in this run), or None."""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(tp) as f:
+            return json.load(f).get("configs", {}).get(name, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
     """One BASELINE shape as a sub-record: same loop, same parity check, HBM roofline."""
     import torch
@@ -393,6 +404,7 @@ def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
                      "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                      "frac": (gbs / float(peaks["hbm_gbs"])) if bound == "hbm" else tf / peak_tf,
                      "hbm_gbs": gbs, "tflops": tf,
+                     "traffic": _static_traffic(name),
                      "algorithmic": {"bytes_per_sample": d * esz + 4, "flops_per_sample": 2 * d * k}},
         "parity_check": par, "final_shift": float(st.shift.item()),
     }
