@@ -273,16 +273,26 @@ struct CentreFromSums {
   }
 };
 
+// STAGED: every CTA first evaluates C' = sums / max(counts, 1) ONCE into shared memory (k*d float64: 128 KB at C2) and
+// all later passes (shift, max |c|, norms, the five layouts) read that copy instead of repeating the float64 division
+// per access — the same quotient, computed once (44 -> ~15 us at k*d = 16384).
+template <bool STAGED>
 __global__ void __launch_bounds__(1024)
 finalize_step_fused_kernel(const double* __restrict__ red, const double* __restrict__ c_in, double* __restrict__ c_out,
                            LoopState* st, unsigned char* pack, PackLayout L) {
-  extern __shared__ double cn_s[];        // [k]
+  extern __shared__ double cn_s[];        // [k] (+ [k*d] staged centres)
   __shared__ double sred[32];
   if (st->done) return;
   const int k = L.k, d = L.d, kd = k * d, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const CentreFromSums cnew{red, kd, d};
+  const CentreFromSums cfs{red, kd, d};
+  double* cs = cn_s + k;
+  if (STAGED) {
+    for (int i = tid; i < kd; i += 1024) cs[i] = cfs(i);
+    __syncthreads();
+  }
+  const CentreFromMemory cmem{cs};
   double acc = 0.0;
-  for (int i = tid; i < kd; i += 1024) { const double df = c_in[i] - cnew(i); acc = fma(df, df, acc); }
+  for (int i = tid; i < kd; i += 1024) { const double df = c_in[i] - (STAGED ? cmem(i) : cfs(i)); acc = fma(df, df, acc); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) sred[wid] = acc;
@@ -292,8 +302,9 @@ finalize_step_fused_kernel(const double* __restrict__ red, const double* __restr
   __syncthreads();
   const bool converged = shift < st->tol;
   if (!converged) {
-    for (int i = blockIdx.x * 1024 + tid; i < kd; i += gridDim.x * 1024) c_out[i] = cnew(i);
-    pack_fused_body(cnew, pack, L, cn_s);
+    for (int i = blockIdx.x * 1024 + tid; i < kd; i += gridDim.x * 1024) c_out[i] = STAGED ? cmem(i) : cfs(i);
+    if (STAGED) pack_fused_body(cmem, pack, L, cn_s);
+    else pack_fused_body(cfs, pack, L, cn_s);
   }
   // the state is written last, by one thread of the last CTA to get here (every CTA has read st->done / st->tol)
   __shared__ bool last;
@@ -428,7 +439,15 @@ int launch_finalize_step(const double* red, const double* c_in, double* c_out, v
   LoopState* st = reinterpret_cast<LoopState*>(state);
   if (k <= 2048 && (long long)k * d <= 65536 && !tc2_shape(d, k, dtype)) {
     int nb = (L.kp * L.dk + 2047) / 2048; if (nb > 16) nb = 16; if (nb < 1) nb = 1;
-    finalize_step_fused_kernel<<<nb, 1024, (size_t)k * 8, s>>>(red, c_in, c_out, st, (unsigned char*)pack, L);
+    const size_t staged_bytes = ((size_t)k + (size_t)k * d) * 8;
+    if (staged_bytes <= 200 * 1024) {
+      if (staged_bytes > 48 * 1024)
+        BKM_CUDA_TRY(cudaFuncSetAttribute(finalize_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)staged_bytes));
+      finalize_step_fused_kernel<true><<<nb, 1024, staged_bytes, s>>>(red, c_in, c_out, st, (unsigned char*)pack, L);
+    } else {
+      finalize_step_fused_kernel<false><<<nb, 1024, (size_t)k * 8, s>>>(red, c_in, c_out, st, (unsigned char*)pack, L);
+    }
     note_launch();
     BKM_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -455,18 +474,32 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
   // The additions run in CTA order (that is what makes a chunk's contribution reproducible); the loads of a
   // batch are independent, so 16 of them are in flight at a time instead of one.
   if (mstep) {
-    for (int i = tid; i < kd; i += nth) {
+    // sums: thread (x, y) of a 32 x 8 block adds the partials y, y + 8, ... of output 32 * block + x (coalesced across
+    // x, 8 independent chains per output instead of one), then the 8 chain sums are added in order y = 0..7: a fixed
+    // order, so a chunk's contribution is bit-reproducible run to run.
+    __shared__ double part_s[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    for (int i0 = blockIdx.x * 32; i0 < kd; i0 += gridDim.x * 32) {
+      const int i = i0 + x;
       double s = 0.0;
-      int g = 0;
-      for (; g + 16 <= sum_parts; g += 16) {
-        PS v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = psum[(size_t)(g + q) * kd + i];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) s += (double)v[q];
+      if (i < kd) {
+        int g = y;
+        for (; g + 24 < sum_parts; g += 32) {
+          const PS v0 = psum[(size_t)g * kd + i], v1 = psum[(size_t)(g + 8) * kd + i];
+          const PS v2 = psum[(size_t)(g + 16) * kd + i], v3 = psum[(size_t)(g + 24) * kd + i];
+          s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+        }
+        for (; g < sum_parts; g += 8) s += (double)psum[(size_t)g * kd + i];
       }
-      for (; g < sum_parts; ++g) s += (double)psum[(size_t)g * kd + i];
-      sums[i] = first ? s : sums[i] + s;
+      part_s[y][x] = s;
+      __syncthreads();
+      if (y == 0 && i < kd) {
+        double t = part_s[0][x];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += part_s[q][x];
+        sums[i] = first ? t : sums[i] + t;
+      }
+      __syncthreads();
     }
     // counts: the last CTAs take them (the first ones already carry the tail of the sums loop)
     for (int i = nth - 1 - tid; i < k; i += nth) {
@@ -500,7 +533,7 @@ __global__ void reduce_partials_kernel(const PS* __restrict__ psum, const int* _
 int launch_reduce_partials(const ChunkArgs& a, int sum_parts, int cnt_parts, int pin_parts, bool mstep, int dtype,
                            double* sums, long long* counts, double* dist_sum, cudaStream_t s) {
   const int kd = a.k * a.d;
-  int nb = (kd + 255) / 256; if (nb > 148) nb = 148; if (nb < 1) nb = 1;
+  int nb = (kd + 31) / 32; if (nb > 592) nb = 592; if (nb < 1) nb = 1;      // blocks of 32 outputs x 8 partial chains
   if (dtype != BKM_F64)
     reduce_partials_kernel<float><<<nb, 256, 0, s>>>((const float*)a.psum, a.pcnt, a.pin, cnt_parts, pin_parts, sum_parts,
                                                      kd, a.k, mstep, sums, counts, dist_sum, a.skip, a.first_chunk, a.counts_f64);

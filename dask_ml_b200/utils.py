@@ -96,10 +96,28 @@ def _timer(name, _logger=None, level="info"):
     start = tic()
     _logger = _logger or logger
     _logger.info("Starting %s", name)
-    yield
+    nvtx = _nvtx()
+    if nvtx is not None:
+        nvtx.range_push(str(name))         # the phases of fit show up as ranges in an Nsight Systems / ncu --nvtx timeline
+    try:
+        yield
+    finally:
+        if nvtx is not None:
+            nvtx.range_pop()
     stop = tic()
     delta = stop - start
     getattr(_logger, level)("Finished %s in %0.4fs", name, delta)
+
+
+def _nvtx():
+    """torch.cuda.nvtx when a CUDA context exists in this process (never initialises one), else None."""
+    try:
+        import torch
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            return torch.cuda.nvtx
+    except Exception:
+        pass
+    return None
 
 
 def _timed(_logger=None, level="info"):
