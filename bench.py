@@ -22,7 +22,7 @@ Numbers reported:
                 device (mismatches must be float64 near-ties; worst relative margin reported) + deferred-row fraction
   configs       the other BASELINE shapes as sub-records, same loop, same parity check: C3 (4.9M x 41, k=100; with N>1
                 the SAME 4.9M rows are split across ranks = strong scaling), C4 (15M x 13, k=20 per GPU = the 8-GPU
-                shard of 120M x 13; weak), C5s (a slice of C5: bf16, d=128, k=1024) when the build supports it
+                shard of 120M x 13; weak), C5 (125M x 128 bf16 rows per GPU in 8 resident chunks, k=1024; `--configs C5s` = an 8M-row slice)
   allreduce_us  N>1: latency of the per-iteration collective on the [k*d+k+1] float64 buffer, CUDA events
   cpu_baseline  the dask-ml path restated without dask (oracle/: scikit-learn float64 E-step + the reference's numba
                 scatter-add, thread pool over row blocks) on a bounded row sample of C2
@@ -56,6 +56,8 @@ CONFIGS = {
                what="KDD-Cup-99-shaped 4,898,431 x 41 float32, k=100 (benchmarks/k_means_kdd.py shape); N>1 splits the SAME rows"),
     "C4": dict(n=15_000_000, d=13, k=20, dtype="f32", scaling="weak", gen="airline", seed=2,
                what="airline-shaped 15M x 13 float32 per GPU, k=20 (the 8-GPU shard of 120M x 13, benchmarks/kmeans_airline.py shape)"),
+    "C5": dict(n=125_000_000, chunks=8, d=128, k=1024, dtype="bf16", scaling="weak", gen="blobs", seed=3,
+               what="C5: 125M x 128 bf16 rows per GPU (1B rows on 8 GPUs) in 8 resident chunks of 15.6M rows, k=1024 (BASELINE configs[4])"),
     "C5s": dict(n=8_000_000, d=128, k=1024, dtype="bf16", scaling="weak", gen="blobs", seed=3,
                 what="slice of C5: 8M x 128 bf16 per GPU, k=1024 (C5 is 125M rows per GPU; samples/s is linear in n)"),
 }
@@ -363,6 +365,7 @@ def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
 
     cfg = CONFIGS[name]
     d, k = cfg["d"], cfg["k"]
+    Xs = None
     if cfg["scaling"] == "strong":
         n_total = cfg["n"]
         per = -(-n_total // world)
@@ -374,11 +377,20 @@ def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
         torch.cuda.empty_cache()
     else:
         n_total = cfg["n"] * world
-        X = synth_config_device(name, cfg["n"], rank, dev)
-    n_local = int(X.shape[0])
-    if d % 4 and be.kernel_family(d, k, X.dtype) == 1:
-        X = be.to_device(X, X.dtype)          # the tensor path wants a 16-byte row pitch (padded view)
-    data = DeviceData([X], be, comm)
+        nch = int(cfg.get("chunks", 1))
+        if nch > 1:
+            # several resident chunks per GPU (each its own allocation), generated with their own seeds
+            per = -(-cfg["n"] // nch)
+            Xs = [synth_config_device(name, min(per, cfg["n"] - c * per), rank * nch + c, dev) for c in range(nch)]
+        else:
+            X = synth_config_device(name, cfg["n"], rank, dev)
+    if Xs is None:
+        if d % 4 and be.kernel_family(d, k, X.dtype) == 1:
+            X = be.to_device(X, X.dtype)          # the tensor path wants a 16-byte row pitch (padded view)
+        Xs = [X]
+    X = Xs[0]
+    n_local = int(sum(int(x.shape[0]) for x in Xs))
+    data = DeviceData(Xs, be, comm)
     init = data.global_rows(list(range(k))).astype(np.float64)
     st = LloydState(data, init)
     steps = max(5, args.steps)
@@ -396,6 +408,7 @@ def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
     bound = "hbm" if t_hbm >= t_tc else "tensor"
     rec = {
         "workload": cfg["what"], "scaling": cfg["scaling"], "n_total": int(n_total), "rows_per_gpu": n_local,
+        "chunks_per_gpu": len(Xs),
         "n_features": d, "n_clusters": k, "dtype": cfg["dtype"], "row_pitch_elems": int(X.stride(0)),
         "steps": steps, "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "samples/s",
         "kernel_family": int(be.kernel_family(d, k, X.dtype)), "kernel_ms": kern_ms,
@@ -408,7 +421,7 @@ def run_config(name, args, be, comm, dev, rank, world, barrier, peaks):
                      "algorithmic": {"bytes_per_sample": d * esz + 4, "flops_per_sample": 2 * d * k}},
         "parity_check": par, "final_shift": float(st.shift.item()),
     }
-    del st, data, X
+    del st, data, X, Xs
     torch.cuda.empty_cache()
     return rec
 
@@ -423,8 +436,8 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per GPU of the headline workload (default: C2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
-    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5s sub-records")
-    ap.add_argument("--configs", default="C3,C4,C5s", help="comma-separated sub-records to run")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5 sub-records")
+    ap.add_argument("--configs", default="C3,C4,C5", help="comma-separated sub-records to run")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 

@@ -10,6 +10,8 @@ REPORTS = {
     "rowpass_mstep_v0": ("prof_rowpass2.ncu-rep", "rowpass_mstep_kernel (early per-warp label-scan version, 4M x 128 bf16, k=1024) — the profile that showed the gather loads were not in flight together"),
     "tc_chunk_C2": ("prof_tc_r02.ncu-rep", "tc_chunk_kernel<true,false> on C2 10M x 64, k=256; ncu --set full --clock-control none --import-source on -k regex:tc_chunk_kernel --launch-skip 3 -c 1 python tests/shape_bench.py C2 --steps 2"),
     "tc_chunk_C3": ("prof_tc_c3_r02.ncu-rep", "tc_chunk_kernel<true,false> on C3 4,898,431 x 41 (pitch 44), k=100, KDD-shaped cluster sizes; same command with C3"),
+    "tc2_assign_C5": ("prof_tc2_c5.ncu-rep", "tc2_assign_kernel on one 15.6M-row chunk of C5 (125M x 128 bf16 per GPU, k=1024, 2 centre slices); ncu --set full --clock-control none -k regex:tc2_assign --launch-skip 6 -c 1 python bench.py --steps 5 --warmup 1 --no-cpu --no-e2e --configs C5"),
+    "rowpass_mstep_C5": ("prof_rowpass_c5.ncu-rep", "rowpass_mstep_kernel (label-indexed M-step row pass) on one 15.6M-row chunk of C5; same command with -k regex:rowpass_mstep"),
     "stream_v3_C4": ("prof_stream3.ncu-rep", "stream2_chunk_kernel<7,20,true> with the shared-memory M-step (lane = feature x row half) on C4 15M x 13, k=20; ncu --set full -k regex:stream2_chunk_kernel --launch-skip 3 -c 1 python tests/shape_bench.py C4 --steps 2"),
 }
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
