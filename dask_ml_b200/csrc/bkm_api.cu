@@ -102,6 +102,7 @@ static int chunk_common(const void* X, long long n, int d, long long ldx, int x_
   a.rec = reinterpret_cast<float4*>((unsigned char*)ws + W.off_rec);
   a.bin_list = (unsigned char*)ws + W.off_bin;
   a.bin_off = (int*)((unsigned char*)ws + W.off_binoff);
+  a.bal = (unsigned char*)ws + W.off_bal;
 
   int family = bkm_kernel_family(d, k, x_dtype, flags);
   if (family < 0) return family;

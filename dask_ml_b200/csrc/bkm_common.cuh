@@ -112,7 +112,7 @@ struct PackHeader {
 static const int kDefaultSMs = 148;
 
 struct WsLayout {
-  size_t off_psum, off_pcnt, off_pin, off_flag, off_defer, off_rec, off_lab, off_bin, off_binoff, total;
+  size_t off_bal, off_psum, off_pcnt, off_pin, off_flag, off_defer, off_rec, off_lab, off_bin, off_binoff, total;
   size_t psum_esz;
   int psum_slots;     // capacity of off_psum in [k*d] slots
   int part_slots;     // capacity of off_pcnt / off_pin (per-CTA counts / distance sums): the largest grid
@@ -136,6 +136,9 @@ static inline WsLayout ws_layout(long long n, int d, int k, int dtype, int sm_co
     W.psum_slots = (int)(sm_count * per_sm);
   }
   size_t o = 0;
+  // FIXED offset (independent of n): the cluster -> warp balance table of the label-indexed M-step pass survives from one
+  // chunk call to the next (16-byte header {magic, k, cluster slices} + one byte per cluster, k <= 4096)
+  W.off_bal = o; o = align_up(o + 16 + 4096, 256);
   W.off_psum = o; o = align_up(o + (size_t)W.psum_slots * slot, 256);
   W.off_pcnt = o; o = align_up(o + (size_t)W.part_slots * k * 4, 256);
   W.off_pin = o;  o = align_up(o + (size_t)W.part_slots * 8, 256);
@@ -182,6 +185,7 @@ struct ChunkArgs {
   float4* rec;        // large-shape tensor path: [S][n] partial arg-min records {m1, m2, label bits, ||x||^2}
   void* bin_list;     // ... M-step row pass: per-tile row bins (4 B per row) and their bucket offsets
   int* bin_off;
+  unsigned char* bal;  // ... and its persistent balance table (WsLayout::off_bal)
   float* xf_out;      // transform variants: output block (rows x k), row pitch xf_ld floats; mode 0 sqrt / 1 squared / 2 rbf
   long long xf_ld;
   int xf_mode;

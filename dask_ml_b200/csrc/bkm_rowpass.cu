@@ -73,10 +73,20 @@ template <> struct RowPiece<__nv_bfloat16, 4> {
 // = row-in-tile | local cluster << 12; tile_off[tile][b] = first position of bucket b, [NB] = valid rows of the tile.
 // One CTA per tile (grid-stride); labels are read once.
 // ------------------------------------------------------------------------------------------
+// The owner warp of a cluster inside its slice comes from the BALANCE TABLE when the previous chunk call left one for
+// this (k, CS) (rowpass_balance_kernel: clusters ranked by size and dealt to the 16 warps in snake order), else it is
+// (c / CS) % NW.  Cluster sizes are heavy-tailed (a centre that covers five blobs owns 5x the mean) and a CTA runs as
+// long as its most loaded warp: 1.25-1.45x the mean with the static map.  The table only moves clusters between warps;
+// the rows of a cluster are still added in row order by ONE warp, so the sums are bit-identical with or without it.
+static const unsigned RP_BAL_MAGIC = 0x62616c31u;     // "bal1"
+
 __global__ void __launch_bounds__(RP_THREADS)
 rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigned* __restrict__ bins, int* __restrict__ tile_off,
-                   const int* skip) {
+                   const unsigned char* __restrict__ bal, int k, const int* skip) {
   if (skip && *skip) return;
+  const unsigned* bh = reinterpret_cast<const unsigned*>(bal);
+  const bool use_bal = bal && bh[0] == RP_BAL_MAGIC && bh[1] == (unsigned)k && bh[2] == (unsigned)c.CS;
+  const unsigned char* btab = bal + 16;
   __shared__ int cntw[RP_NW][RP_MAXB];          // pass 1: rows of (warp, bucket); pass 2: running write position
   __shared__ int base_s[RP_MAXB + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,7 +103,9 @@ rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigne
       const long long r = r0 + warp * 256 + u * 32 + lane;
       const int ml = r < n ? __ldg(labels + r) : -1;
       cl[u] = ml >> c.LCS;
-      bk[u] = ml < 0 ? -1 : ((ml & (c.CS - 1)) * RP_NW + (cl[u] & (RP_NW - 1)));
+      int ow = cl[u] & (RP_NW - 1);
+      if (use_bal && ml >= 0) ow = min((int)btab[ml], RP_NW - 1);
+      bk[u] = ml < 0 ? -1 : ((ml & (c.CS - 1)) * RP_NW + ow);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -130,6 +142,38 @@ rowpass_bin_kernel(const int* __restrict__ labels, long long n, RpCfg c, unsigne
       }
       __syncwarp();
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Step 3 (after the M-step): rebuild the balance table from THIS call's per-cluster counts for the next call.
+// Block cs ranks the KL clusters of its slice by size (ties by index) and deals rank r to warp r % 16 on even rounds,
+// 15 - r % 16 on odd rounds.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+rowpass_balance_kernel(const int* __restrict__ pcnt, int parts, int k, RpCfg c, unsigned char* bal, const int* skip) {
+  if (skip && *skip) return;
+  extern __shared__ int sz_s[];                    // [KL]
+  const int cs = blockIdx.x, CS = c.CS, KL = c.KL;
+  for (int i = threadIdx.x; i < KL; i += blockDim.x) {
+    const int cg = i * CS + cs;
+    int t = 0;
+    if (cg < k) for (int p = 0; p < parts; ++p) t += pcnt[(size_t)p * k + cg];
+    sz_s[i] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KL; i += blockDim.x) {
+    const int cg = i * CS + cs;
+    if (cg >= k) continue;
+    const int mine = sz_s[i];
+    int rank = 0;
+    for (int j = 0; j < KL; ++j) rank += (sz_s[j] > mine || (sz_s[j] == mine && j < i)) ? 1 : 0;
+    const int r = rank & (RP_NW - 1);
+    bal[16 + cg] = (unsigned char)(((rank / RP_NW) & 1) ? RP_NW - 1 - r : r);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned* bh = reinterpret_cast<unsigned*>(bal);
+    bh[0] = RP_BAL_MAGIC; bh[1] = (unsigned)k; bh[2] = (unsigned)CS; bh[3] = 0u;
   }
 }
 
@@ -307,7 +351,7 @@ int launch_rowpass_mstep(const ChunkArgs& a, int x_dtype, int sm_count, int* par
   unsigned* bins = reinterpret_cast<unsigned*>(a.bin_list);
   int* tile_off = a.bin_off;
   long long nbk = c.ntiles < (long long)sm_count * 4 ? c.ntiles : (long long)sm_count * 4;
-  rowpass_bin_kernel<<<(int)nbk, RP_THREADS, 0, s>>>(a.labels, a.n, c, bins, tile_off, a.skip);
+  rowpass_bin_kernel<<<(int)nbk, RP_THREADS, 0, s>>>(a.labels, a.n, c, bins, tile_off, a.k <= 4096 ? a.bal : nullptr, a.k, a.skip);
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
 #define RP_GO(F)                                                                                                   \
@@ -320,6 +364,11 @@ int launch_rowpass_mstep(const ChunkArgs& a, int x_dtype, int sm_count, int* par
 #undef RP_GO
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());
+  if (a.bal && a.k <= 4096) {
+    rowpass_balance_kernel<<<c.CS, 1024, (size_t)c.KL * sizeof(int), s>>>(a.pcnt, c.RB, a.k, c, a.bal, a.skip);
+    note_launch();
+    BKM_CUDA_TRY(cudaGetLastError());
+  }
   *parts_out = c.RB;
   return 0;
 }

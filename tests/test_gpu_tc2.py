@@ -146,3 +146,32 @@ def test_tc2_fit_matches_oracle(be, oracle):
     np.testing.assert_allclose(km.cluster_centers_, C, rtol=1e-4, atol=1e-4)
     pred = km.predict(X).compute()
     assert int((pred != got).sum()) <= 3
+
+
+def test_tc2_fit_chunked_equals_single_chunk(be, oracle):
+    """The C5 layout of bench.py: several resident bf16 chunks per GPU (ragged sizes).  Labels / inertia / centres must
+    not depend on how the rows are chunked (up to the fp32 partial sums), and predict / transform follow."""
+    import torch
+    from dask_ml_b200.chunked import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    n, d, k = 41000, 128, 600
+    X, x, _ = _data(be, n, d, k, 91)
+    init = X[:k].float().cpu().numpy()
+    one = KMeans(n_clusters=k, init=init, max_iter=4, tol=0.0).fit(X)
+    cuts = [0, 9000, 9001, 25000, n]
+    parts = ChunkedArray([X[a:b] for a, b in zip(cuts, cuts[1:])])
+    many = KMeans(n_clusters=k, init=init, max_iter=4, tol=0.0).fit(parts)
+    assert many.n_iter_ == one.n_iter_
+    la, lb = one.labels_.compute(), many.labels_.compute()
+    assert int((la != lb).sum()) <= 3
+    assert abs(many.inertia_ - one.inertia_) / one.inertia_ < 1e-5
+    np.testing.assert_allclose(many.cluster_centers_, one.cluster_centers_, rtol=2e-3, atol=2e-3)
+    # predict = labels of the fitted centres on the same rows (Q4: shift > 1e-7 -> labels_ come from a re-label)
+    pred = many.predict(parts).compute()
+    assert int((pred != lb).sum()) <= 3
+    # against the float64 arg-min of the final centres
+    C = torch.as_tensor(many.cluster_centers_.astype(np.float64)).to(be.device)
+    want, margin = _exact(X.double(), C)
+    bad = torch.as_tensor(pred).to(be.device).long() != want
+    assert int(bad.sum()) == 0 or bool((margin[bad] <= 1e-9 * ((X.double() ** 2).sum(1)[bad] + (C ** 2).sum(1).max())).all())
