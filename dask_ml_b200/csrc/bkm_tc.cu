@@ -115,6 +115,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // warp) in g_tc_abort and returns; every later wait returns at once, the kernel drains with garbage and
 // the host reports the code (bkm_debug_abort_code).
 __device__ unsigned int g_tc_abort = 0;
+#ifndef BKM_TC_PSLEEP
+#define BKM_TC_PSLEEP 0
+#endif
 #ifndef BKM_TRACE
 #define BKM_TRACE 0
 #endif
@@ -385,41 +388,53 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
       const uint32_t mkblk = (uint32_t)MR * 128u;
       const uint32_t mbytes = (uint32_t)KB * mkblk;
       const long long m_total = cfg.mring ? qpt * my_tiles : 0;
+      // Ring positions are carried as counters (stage / slot, phase bit, tile, quarter): the poll below runs every
+      // ~100 cycles.  With `ait % NST`, `ait / NST`, `mi / qpt` (64-bit divisions by run-time values, a few hundred
+      // cycles each in software) one poll took ~2000 cycles, and that reaction time sat in BOTH ring periods:
+      // (reaction + TMA latency + consumer) / 2 slots.
       long long ait = 0, mi = 0;
+      int a_stage = 0;                      // ait % NST
+      uint32_t a_par = 1;                   // ((ait / NST) & 1) ^ 1
+      long long a_tile = blockIdx.x;        // blockIdx.x + ait * gridDim.x
+      int m_slot = 0;                       // mi & 1
+      uint32_t m_par = 1;                   // ((mi >> 1) & 1) ^ 1
+      long long m_tile_i = 0;               // mi / qpt
+      int m_q = 0;                          // mi % qpt
+      long long m_tile = blockIdx.x;        // blockIdx.x + m_tile_i * gridDim.x
       uint32_t idle = 0;
       unsigned long long idle_t0 = 0;
 #pragma unroll 1
       while (ait < my_tiles || mi < m_total) {
         bool progressed = false;
         if (ait < my_tiles) {
-          const int stage = (int)(ait % NST);
-          if (mbar_test(BAR(BAR_X_EMPTY + stage), (uint32_t)(((ait / NST) & 1) ^ 1))) {
-            const long long tile = blockIdx.x + ait * gridDim.x;
+          if (mbar_test(BAR(BAR_X_EMPTY + a_stage), a_par)) {
             TRACE(0, ait);
             if (ait + PF < my_tiles)
-              for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((tile + (long long)PF * gridDim.x) * BM));
-            mbar_expect_tx(BAR(BAR_X_FULL + stage), stage_bytes);
+              for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&tm_x, kb * 32, (int)((a_tile + (long long)PF * gridDim.x) * BM));
+            mbar_expect_tx(BAR(BAR_X_FULL + a_stage), stage_bytes);
             for (int kb = 0; kb < KB; ++kb)
-              tma_load_2d(s_x + stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + stage),
-                          kb * 32, (int)(tile * BM));
+              tma_load_2d(s_x + a_stage * stage_bytes + (uint32_t)kb * KBLK_BYTES, &tm_x, BAR(BAR_X_FULL + a_stage),
+                          kb * 32, (int)(a_tile * BM));
             ++ait;
+            a_tile += gridDim.x;
+            if (++a_stage == NST) { a_stage = 0; a_par ^= 1u; }
             progressed = true;
           }
         }
-        if (mi < m_total && (mi / qpt) < ait) {
-          const int slot = (int)(mi & 1);
-          if (mbar_test(BAR(BAR_M_EMPTY + slot), (uint32_t)(((mi >> 1) & 1) ^ 1))) {
-            const long long tile = blockIdx.x + (mi / qpt) * gridDim.x;
-            mbar_expect_tx(BAR(BAR_M_FULL + slot), mbytes);
+        if (mi < m_total && m_tile_i < ait) {
+          if (mbar_test(BAR(BAR_M_EMPTY + m_slot), m_par)) {
+            mbar_expect_tx(BAR(BAR_M_FULL + m_slot), mbytes);
             for (int kb = 0; kb < KB; ++kb)
-              tma_load_2d(s_m + slot * mbytes + (uint32_t)kb * mkblk, &tm_xm, BAR(BAR_M_FULL + slot), kb * 32,
-                          (int)(tile * BM + (mi % qpt) * MR));
+              tma_load_2d(s_m + m_slot * mbytes + (uint32_t)kb * mkblk, &tm_xm, BAR(BAR_M_FULL + m_slot), kb * 32,
+                          (int)(m_tile * BM + m_q * MR));
             ++mi;
+            if (++m_q == qpt) { m_q = 0; ++m_tile_i; m_tile += gridDim.x; }
+            if ((m_slot ^= 1) == 0) m_par ^= 1u;
             progressed = true;
           }
         }
         if (progressed) { idle = 0; idle_t0 = 0; continue; }
-        __nanosleep(64);
+        if (BKM_TC_PSLEEP > 0) __nanosleep(BKM_TC_PSLEEP);
         if ((++idle & 255) == 255) {
           const unsigned long long now = tc_now_ns();
           if (idle_t0 == 0) idle_t0 = now;
@@ -461,7 +476,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         // the buffer was last used by unit g-NBUF, drained by epilogue set ((g-NBUF)/U) & 1, which signals the
         // barrier of (its set, the buffer, the issuer of the buffer's next unit = this warp)
         const long long gp = g - NBUF;
-        const int eb = (int)((gp / U) & 1) * NBUF + buf;
+        const int eb = (int)((U == 2 ? (gp >> 1) : gp) & 1) * NBUF + buf;
         mbar_wait(BAR(BAR_ACC_EMPTY + 2 * eb + (warp - 1)), (empty_ph >> eb) & 1u);
         empty_ph ^= 1u << eb;
       }
@@ -509,9 +524,10 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     for (int q = 0; q < 8; ++q) xoff[q] = sw_chunk(r, q);
 #pragma unroll 1
     for (long long it = 0; it < my_tiles; ++it) {
-      const int stage = (int)(it % NST);
+      // (32-bit arithmetic: a 64-bit division by a run-time value costs a few hundred cycles)
+      const int stage = (int)((unsigned)it % (unsigned)NST);
       // ---- s X -> fp16 (hi, lo) pairs in TMEM, and ||s x||^2 ----
-      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));
+      mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)(((unsigned)it / (unsigned)NST) & 1u));
       mbar_wait(BAR(BAR_XOP_EMPTY + (it & 1)), (uint32_t)(((it >> 1) & 1) ^ 1));
       tc_fence_after();
       if (r == 0) TRACE(1, it);
@@ -669,7 +685,9 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
         if (r == 0) TRACE(7 + 2 * u, it);
         const uint32_t tbase = tmem + lane_addr + (uint32_t)buf * 128u;
         uint32_t v0[16], v1[16];
-        // the next chunk's load is in flight while the current one is reduced
+        // the next chunk's load is in flight while the current one is reduced.  (Measured r02: two chunks per
+        // tcgen05.wait::ld do NOT help — a warp's TMEM loads are served one after the other, ~2 KB per 300 cycles, and 8
+        // epilogue warps together already draw ~54 of the 64 B/clk the SM's TMEM read path delivers.)
         TC_LD16(tbase, v0);
 #pragma unroll 1
         for (int c = 0; c < nch; c += 2) {
@@ -887,11 +905,11 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const int lb = (int)(it % NLAB);
-      const int stage = (int)(it % NST);
+      const int stage = (int)((unsigned)it % (unsigned)NST);
       // every warp polls on its own: a barrier across the 16 warps would make each step as slow as its
       // most loaded warp
       mbar_wait_sleep(BAR(BAR_LAB_FULL + lb), (uint32_t)((it / NLAB) & 1));
-      if (direct) mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)((it / NST) & 1));   // completed long ago: acquire only
+      if (direct) mbar_wait(BAR(BAR_X_FULL + stage), (uint32_t)(((unsigned)it / (unsigned)NST) & 1u));   // completed long ago: acquire only
       if (wm == 0 && lane == 0) TRACE(12, it);
 #pragma unroll 1
       for (int h = 0; h < 4; ++h) {
