@@ -52,6 +52,13 @@ SIGNATURES = {
                                    _c_void_p]),
     "bkm_finalize": (_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _int, _int, _c_void_p]),
     "bkm_check_finite": (_int, [_c_void_p, _i64, _int, _i64, _int, _c_void_p, _c_void_p]),
+    "bkm_p2p_mailbox_bytes": (_int, [_int, _i64, ctypes.POINTER(ctypes.c_size_t)]),
+    "bkm_p2p_alloc": (_int, [ctypes.c_size_t, ctypes.POINTER(_c_void_p)]),
+    "bkm_p2p_free": (_int, [_c_void_p]),
+    "bkm_p2p_export": (_int, [_c_void_p, _c_void_p]),
+    "bkm_p2p_import": (_int, [_c_void_p, ctypes.POINTER(_c_void_p)]),
+    "bkm_p2p_close": (_int, [_c_void_p]),
+    "bkm_allreduce_p2p": (_int, [_c_void_p, _i64, _c_void_p, _int, _int, _i64, ctypes.c_uint, _c_void_p]),
     "bkm_launch_count": (_i64, []),
     "bkm_debug_fallback_count": (_i64, []),
     "bkm_debug_abort_code": (ctypes.c_uint, []),

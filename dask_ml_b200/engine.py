@@ -11,6 +11,7 @@ One process drives one GPU.  With ``torch.distributed`` initialised each rank ho
 chunks; without it the engine is single-GPU.
 """
 import ctypes
+import os
 import weakref
 
 import numpy as np
@@ -45,6 +46,10 @@ class Comm(object):
 
     def allreduce_sum_(self, t):
         if self.world > 1:
+            p2p = _p2p_state(self) if (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()) else None
+            if p2p is not None and t.numel() <= p2p.max_elems:
+                p2p.allreduce_(t)             # one kernel over NVLink peer memory, sums added in rank order
+                return t
             import torch.distributed as dist
 
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -67,6 +72,98 @@ class Comm(object):
         box = [obj]
         dist.broadcast_object_list(box, src=src)
         return box[0]
+
+
+class _P2PAllReduce(object):
+    """The Lloyd loop's per-iteration collective over NVLink peer memory (bkm_p2p.cu): every rank owns a mailbox that all
+    peers of the node have opened through CUDA IPC.  Built once per process (collectively, on first use); any failure —
+    ranks on different hosts, IPC unavailable, BKM_P2P=0 — leaves NCCL in charge."""
+
+    MAX_ELEMS = 1 << 16          # float64 elements per slot: k*d + k + 1 of every shape of the fused kernels
+
+    def __init__(self, comm, device):
+        import socket
+
+        self.lib = _lib.load()
+        self.rank, self.world = comm.rank, comm.world
+        self.device = device
+        self.max_elems = self.MAX_ELEMS
+        self.seq = 0
+        self.box = ctypes.c_void_p(0)
+        self.peers = []
+        ok = os.environ.get("BKM_P2P", "1") != "0" and self.world <= 64
+        hosts = comm.allgather_obj(socket.gethostname())
+        ok = ok and len(set(hosts)) == 1
+        handle = None
+        if ok:
+            try:
+                with torch.cuda.device(device):
+                    nb = ctypes.c_size_t(0)
+                    _lib.check(self.lib.bkm_p2p_mailbox_bytes(self.world, self.max_elems, ctypes.byref(nb)), "bkm_p2p_mailbox_bytes")
+                    _lib.check(self.lib.bkm_p2p_alloc(nb, ctypes.byref(self.box)), "bkm_p2p_alloc")
+                    buf = ctypes.create_string_buffer(64)
+                    _lib.check(self.lib.bkm_p2p_export(self.box, buf), "bkm_p2p_export")
+                    handle = bytes(buf.raw)
+            except Exception:
+                handle = None
+        handles = comm.allgather_obj(handle)                     # collective even when this rank failed
+        ptrs = []
+        good = all(h is not None for h in handles)
+        if good:
+            try:
+                with torch.cuda.device(device):
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            ptrs.append(int(self.box.value))
+                        else:
+                            pp = ctypes.c_void_p(0)
+                            _lib.check(self.lib.bkm_p2p_import(ctypes.create_string_buffer(h, 64), ctypes.byref(pp)), "bkm_p2p_import")
+                            self.peers.append(pp)
+                            ptrs.append(int(pp.value))
+            except Exception:
+                good = False
+        self.ready = all(comm.allgather_obj(bool(good)))         # everyone or no one
+        if self.ready:
+            self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+            import atexit
+
+            atexit.register(self.close)
+
+    def allreduce_(self, t):
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bkm_allreduce_p2p(
+                ctypes.c_void_p(t.data_ptr()), t.numel(), ctypes.c_void_p(self.table.data_ptr()), self.rank, self.world,
+                self.max_elems, ctypes.c_uint(self.seq & 0xFFFFFFFF),
+                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "bkm_allreduce_p2p")
+
+    def close(self):
+        try:
+            torch.cuda.synchronize(self.device)
+            for pp in self.peers:
+                self.lib.bkm_p2p_close(pp)
+            self.peers = []
+            if self.box.value:
+                self.lib.bkm_p2p_free(self.box)
+                self.box = ctypes.c_void_p(0)
+        except Exception:
+            pass
+        self.ready = False
+
+
+_P2P = {}
+
+
+def _p2p_state(comm):
+    """The process-wide peer-memory all-reduce of the current CUDA device, or None (set up collectively on first use)."""
+    if not torch.cuda.is_available():
+        return None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = _P2P.get(dev)
+    if st is None:
+        st = _P2PAllReduce(comm, dev)
+        _P2P[dev] = st
+    return st if st.ready else None
 
 
 class CudaBackend(object):

@@ -180,6 +180,23 @@ int bkm_make_blobs_chunk(void* X, int64_t* y, int64_t n, int d, int64_t ldx, int
 int bkm_check_finite(const void* X, int64_t n, int d, int64_t ldx, int x_dtype,
                      int* flag, void* stream);
 
+/* ---- the per-iteration collective over NVLink peer memory (N > 1 GPUs of one node) --------------------------------
+ * Replaces the `da.atop(..., sum)` / bincount fold across workers (k_means.py:545-550), i.e. the all-reduce of
+ * [k*d sums | k counts | inertia].  Every rank owns a MAILBOX (bkm_p2p_mailbox_bytes / bkm_p2p_alloc: one cudaMalloc
+ * allocation, zeroed), exports it (64-byte IPC handle), opens every peer's (bkm_p2p_import) and passes the device array
+ * of the `world` mailbox pointers to bkm_allreduce_p2p: one kernel pushes `buf` into a slot of every mailbox, raises a
+ * flag, waits for all flags in its own mailbox (2 s wall-clock limit: a timeout poisons buf[0] with NaN) and adds the slots
+ * in RANK order — every rank ends with bit-identical sums.  `seq` = 1, 2, 3, ... the call number, identical on all ranks;
+ * n <= max_elems (the slot size the mailboxes were sized for). */
+int bkm_p2p_mailbox_bytes(int world, int64_t max_elems, size_t* nbytes);
+int bkm_p2p_alloc(size_t nbytes, void** dev_ptr);
+int bkm_p2p_free(void* dev_ptr);
+int bkm_p2p_export(void* dev_ptr, void* handle64_host);
+int bkm_p2p_import(const void* handle64_host, void** dev_ptr);
+int bkm_p2p_close(void* dev_ptr);
+int bkm_allreduce_p2p(double* buf, int64_t n, void* const* mailboxes_dev, int rank, int world, int64_t max_elems,
+                      unsigned int seq, void* stream);
+
 /* Number of kernel launches this library has enqueued since load (for bench accounting). */
 int64_t bkm_launch_count(void);
 /* Number of chunk calls whose shape belongs to the tcgen05 / streaming family but whose rows were not 16-byte aligned

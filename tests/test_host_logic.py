@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     from dask_ml_b200 import _lib
 
     hdr = open(os.path.join(ROOT, "include", "bkm_b200.h")).read()
-    declared = set(re.findall(r"\b(bkm_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(bkm_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     lib = _lib.load()
     for name in declared:
