@@ -660,9 +660,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 transform_kernel(const T* __restrict__ X, long long n, int d, long long ldx,
                  const unsigned char* __restrict__ pack, PackLayout L, T* __restrict__ out, long long ld_out, int mode,
-                 double gamma) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int TR = 64;
+                 double gamma, int TR) {
+  extern __shared__ __align__(16) unsigned char smem[];   // TR rows per tile: 64, fewer for very wide rows
   const int k = L.k, d4 = L.d4;
   T* xs = reinterpret_cast<T*>(smem);                // [TR][d4+1]
   T* xn = xs + TR * (d4 + 1);                        // [TR]
@@ -704,16 +703,19 @@ int launch_transform(const void* X, long long n, int d, long long ldx, int dtype
                      cudaStream_t s) {
   if (n == 0) return 0;
   PackLayout L = pack_layout(k, d, dtype);
-  long long ntiles = (n + 63) / 64;
-  long long grid = (long long)sm_count * 4; if (grid > ntiles) grid = ntiles;
   size_t esz = dtype == BKM_F64 ? 8 : 4;
-  size_t smem = (size_t)64 * (L.d4 + 1) * esz + 64 * esz + 16;
+  int TR = 64;                                   // rows per tile; wide rows (d in the hundreds / thousands) take fewer
+  while (TR > 1 && (size_t)TR * (L.d4 + 1) * esz + TR * esz + 16 > 200 * 1024) TR >>= 1;
+  size_t smem = (size_t)TR * (L.d4 + 1) * esz + TR * esz + 16;
+  if (smem > 227 * 1024) return BKM_EUNSUPPORTED;
+  long long ntiles = (n + TR - 1) / TR;
+  long long grid = (long long)sm_count * 4; if (grid > ntiles) grid = ntiles;
   if (dtype == BKM_F32) {
     BKM_CUDA_TRY(cudaFuncSetAttribute(transform_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    transform_kernel<float><<<(int)grid, 256, smem, s>>>((const float*)X, n, d, ldx, (const unsigned char*)pack, L, (float*)out, ld_out, mode, gamma);
+    transform_kernel<float><<<(int)grid, 256, smem, s>>>((const float*)X, n, d, ldx, (const unsigned char*)pack, L, (float*)out, ld_out, mode, gamma, TR);
   } else {
     BKM_CUDA_TRY(cudaFuncSetAttribute(transform_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    transform_kernel<double><<<(int)grid, 256, smem, s>>>((const double*)X, n, d, ldx, (const unsigned char*)pack, L, (double*)out, ld_out, mode, gamma);
+    transform_kernel<double><<<(int)grid, 256, smem, s>>>((const double*)X, n, d, ldx, (const unsigned char*)pack, L, (double*)out, ld_out, mode, gamma, TR);
   }
   note_launch();
   BKM_CUDA_TRY(cudaGetLastError());

@@ -35,6 +35,12 @@ SHAPES = [
     (300, 128, 300, "float32"),     # k*d too large for the smem-resident mode -> GLOBAL mode
     (100, 7, 1, "float32"),
     (5, 3, 2, "float32"),
+    # wide rows (the reference works for any d, e.g. 784 pixels): the generic kernel shrinks its row tile
+    (600, 256, 12, "float32"),
+    (500, 784, 10, "float32"),
+    (300, 1024, 5, "float32"),
+    (400, 784, 10, "float64"),
+    (200, 1024, 7, "float64"),
 ]
 
 

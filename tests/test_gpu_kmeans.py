@@ -359,3 +359,26 @@ def test_host_resident_streaming_on_the_gpu(oracle):
     assert int((b.predict(Xh).compute() != a.predict(X).compute()).sum()) == 0
     tr = b.transform(Xh).compute()
     np.testing.assert_allclose(tr, a.transform(X).compute(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_fit_predict_transform_wide_rows(oracle, dtype):
+    """784 features (the MNIST shape the reference's users cluster): fit / predict / transform against the oracle."""
+    from dask_ml_b200 import ChunkedArray
+    from dask_ml_b200.cluster import KMeans
+
+    rng = np.random.RandomState(5)
+    n, d, k = 3000, 784, 10
+    cent = rng.uniform(0, 1, size=(k, d))
+    X = (cent[rng.randint(0, k, size=n)] + 0.1 * rng.standard_normal((n, d))).astype(dtype)
+    init = X[:k].copy()
+    km = KMeans(k, init=init, max_iter=5, tol=0.0).fit(ChunkedArray.from_array(X, 1100))
+    lab, inertia, C, n_iter = oracle.kmeans_single_lloyd(oracle.to_blocks(X, 1100), k, init=init, max_iter=5, tol=0.0)
+    assert km.n_iter_ == n_iter
+    assert int((km.labels_.compute() != np.concatenate(lab)).sum()) == 0
+    assert abs(km.inertia_ - inertia) / inertia < 1e-5
+    np.testing.assert_allclose(km.cluster_centers_, C, rtol=1e-4, atol=1e-5)
+    assert int((km.predict(X).compute() != np.concatenate(lab)).sum()) == 0
+    T = km.transform(X[:500]).compute()
+    want = np.sqrt(((X[:500, None, :].astype(np.float64) - km.cluster_centers_[None].astype(np.float64)) ** 2).sum(-1))
+    np.testing.assert_allclose(T, want, rtol=2e-4, atol=1e-4)
