@@ -456,3 +456,37 @@ def test_baseline_size_parity(be, name, n, d, k):
     if be.kernel_family(d, k, torch.float32) == 1:
         # the rounding bound tau defers only a small fraction of rows to the float64 re-check
         assert be.deferred_rows(n, d, k, torch.float32) < 0.01 * n
+
+
+@pytest.mark.parametrize("d,k,dtype_name", [(32, 64, "float32"), (13, 20, "float32"), (64, 256, "float32"), (128, 600, "bfloat16")])
+def test_sums_with_a_dominant_cluster_and_offset_data(be, d, k, dtype_name):
+    """The fused kernels keep per-CTA (per-warp) partial sums in fp32 and widen them to float64 once per chunk call
+    (the reference accumulates in float64, k_means.py:576).  Worst case for that: one cluster owns 90 % of 2M rows and
+    the data sit far from the origin.  The sums must still agree with the float64 sums of the SAME labels to ~1e-5 of
+    the data's magnitude (the centres move by less than 1e-3 of the cluster's standard deviation)."""
+    import torch
+
+    dtype = getattr(torch, dtype_name)
+    n = 2_000_000
+    g = torch.Generator(device=be.device).manual_seed(d * 1000 + k)
+    cent = torch.empty((k, d), device=be.device).uniform_(-3, 3, generator=g) + 100.0
+    which = torch.where(torch.rand(n, device=be.device, generator=g) < 0.9, torch.zeros(n, device=be.device, dtype=torch.long),
+                        torch.randint(0, k, (n,), device=be.device, generator=g))
+    X = (cent[which] + torch.randn((n, d), device=be.device, generator=g)).to(dtype)
+    x = be.to_device(X, dtype)
+    C = cent.double().contiguous()
+    pack = be.pack_centers(C, dtype)
+    labels = be.empty((n,), torch.int32)
+    sums = be.zeros((k * d,), torch.float64); counts = be.zeros((k,), torch.int64)
+    be.lloyd_chunk(x, pack, k, labels, None, sums, counts, None)
+    torch.cuda.synchronize()
+    lab = labels.long()
+    want = torch.zeros((k, d), dtype=torch.float64, device=be.device).index_add_(0, lab, X.double())
+    wcnt = torch.bincount(lab, minlength=k)
+    assert torch.equal(counts, wcnt)
+    got = sums.view(k, d)
+    scale = (X.double().abs().max() * wcnt.clamp(min=1).double())[:, None]        # |x| * rows of the cluster
+    rel = ((got - want).abs() / scale).max()
+    assert float(rel) < 1e-5, float(rel)
+    newC = got / wcnt.clamp(min=1).double()[:, None]
+    assert float((newC - want / wcnt.clamp(min=1).double()[:, None]).abs().max()) < 1e-3
