@@ -616,6 +616,8 @@ def main():
         "traffic": traffic, "traffic_source": "static: ncu --set full capture committed under profiles/ (not measured in this run)",
         "peak_source": peak_note, "kernel_ms": kern_ms,
         "kernel": "tc_chunk_kernel<true,false> (tcgen05 split-fp16 fused E+M) + tc_recheck + reduce_partials",
+        "limiter": "three 128-column TMEM accumulator buffers x (epilogue ~3.0-3.6k cycles at ~6.8 B/clk of TMEM reads per warp "
+                   "+ MMA refill ~1.0-1.5k) per 2-unit tile; tensor pipe 43 %, issue slots 71 % (DESIGN.md (d), profiles/r02_ncu_tc_chunk_C2.md)",
         "issued": {"tflops": ach_tf * issued_ratio, "frac": ach_tf * issued_ratio / peak_tf,
                    "note": "tensor-pipe work actually issued: 3 fp16 products + ||c||^2 step per algorithmic product"},
         "hbm": {"achieved": ach_gbs, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
