@@ -118,6 +118,9 @@ __device__ unsigned int g_tc_abort = 0;
 #ifndef BKM_TC_PSLEEP
 #define BKM_TC_PSLEEP 0
 #endif
+#ifndef BKM_EXP_1P
+#define BKM_EXP_1P 0
+#endif
 #ifndef BKM_TRACE
 #define BKM_TRACE 0
 #endif
@@ -494,6 +497,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll
         for (int s = 0; s < 4; ++s)
           if (s < KS) mma_f16_ts(d_t, xhi_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, s > 0 ? 1u : 0u);
+#if !BKM_EXP_1P      // (measurement knob BKM_EXP_1P=1: hi x hi product only — how fast would a one-product first pass be?)
         // Xhi . Blo
 #pragma unroll
         for (int s = 0; s < 4; ++s)
@@ -502,6 +506,7 @@ tc_chunk_kernel(ChunkArgs a, TcCfg cfg, const __grid_constant__ CUtensorMap tm_x
 #pragma unroll
         for (int s = 0; s < 4; ++s)
           if (s < KS) mma_f16_ts(d_t, xlo_t + (uint32_t)s * 8u, dbh + (uint64_t)(s * 2), idesc, 1u);
+#endif
         mma_tf32_ss(d_t, dones, dcn + (uint64_t)(rowoff >> 6), make_idesc_tf32(ncols), 1u);     // + s^2 ||c_j||^2
         tc_commit(BAR(BAR_ACC_FULL + (int)(it & 1) * NBUF + buf));
         tc_commit(BAR(BAR_XOP_EMPTY + (it & 1)));      // one arrival per unit: the tile's X operands are free after U of them
