@@ -205,6 +205,7 @@ class CudaBackend(object):
                    "bkm_workspace_bytes")
         if ws is None or ws.numel() < nbytes.value:
             ws = torch.empty(int(nbytes.value * 1.25) + (1 << 20), dtype=torch.uint8, device=self.device)
+            ws[:8192].zero_()        # the persistent header (balance table of the M-step row pass) starts out empty
             self._ws["buf"] = ws
         return ws
 

@@ -86,7 +86,9 @@ int bkm_centers_pack_bytes(int k, int d, int x_dtype, size_t* out);
 int bkm_pack_centers(const double* centers64, int k, int d, int x_dtype,
                      void* pack, size_t pack_bytes, void* stream);
 
-/* Scratch for per-CTA partial sums / counts / inertia of one chunk call. */
+/* Scratch for per-CTA partial sums / counts / inertia of one chunk call.  The first 8 KB are a PERSISTENT header (the
+ * cluster -> warp balance table the label-indexed M-step pass leaves for the next call): zero them once when the buffer
+ * is allocated and otherwise leave them alone; everything behind is overwritten by every call. */
 int bkm_workspace_bytes(int64_t n, int d, int k, int x_dtype, size_t* out);
 
 /* ---- fused E+M step for one row chunk ----------------------------------------------
