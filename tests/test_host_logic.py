@@ -264,3 +264,49 @@ def test_host_resident_streaming_gives_the_same_fit(cpu_engine, oracle):
     c = KMeans(4, init="k-means||", random_state=0, oversampling_factor=6, max_iter=5).fit(Xh)
     d = KMeans(4, init="k-means||", random_state=0, oversampling_factor=6, max_iter=5).fit(X)
     np.testing.assert_allclose(c.cluster_centers_, d.cluster_centers_, rtol=1e-9)
+
+
+def test_metrics_operators_host_logic(monkeypatch):
+    """dask_ml/metrics/pairwise.py:55-139, 172-195 on the checker backend: blocks of 256 columns, Y=None, caller-supplied
+    norms, dtype promotion, rbf gamma default, the error contract (the GPU suite repeats the numerics on the device)."""
+    import sklearn.metrics.pairwise as skp
+    from oracle_backend import OracleBackend
+    from dask_ml_b200 import ChunkedArray, metrics
+    from dask_ml_b200.cluster import k_means as km
+
+    monkeypatch.setattr(km, "_BACKEND_FACTORY", OracleBackend)
+    rng = np.random.RandomState(3)
+    X = rng.standard_normal((700, 9)).astype(np.float32)
+    Y = rng.standard_normal((300, 9)).astype(np.float32)          # > 256 rows: two column blocks
+    Xc = ChunkedArray.from_array(X, 256)
+    D = metrics.euclidean_distances(Xc, Y).compute()
+    assert D.dtype == np.float32 and D.shape == (700, 300)
+    np.testing.assert_allclose(D, skp.euclidean_distances(X, Y), rtol=1e-4, atol=1e-4)
+    D2 = metrics.euclidean_distances(Xc, Y, squared=True).compute()
+    np.testing.assert_allclose(D2, skp.euclidean_distances(X, Y, squared=True), rtol=1e-4, atol=1e-3)
+    # Y = None: X against itself; float64 Y promotes the result
+    S = metrics.euclidean_distances(X[:100]).compute()
+    np.testing.assert_allclose(S, skp.euclidean_distances(X[:100]), rtol=1e-3, atol=5e-3)
+    assert metrics.euclidean_distances(X[:50], Y.astype(np.float64)).compute().dtype == np.float64
+    # caller-supplied norms are USED (pairwise.py:72-91): wrong norms give the reference's (wrong) numbers
+    yy = (Y.astype(np.float64) ** 2).sum(1) + 1.0
+    got = metrics.euclidean_distances(X[:64], Y, Y_norm_squared=yy, squared=True).compute()
+    want = skp.euclidean_distances(X[:64].astype(np.float64), Y.astype(np.float64), squared=True) + 1.0
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3)
+    with pytest.raises(ValueError):
+        metrics.euclidean_distances(X[:10], Y, Y_norm_squared=np.ones(7))
+    with pytest.raises(ValueError):
+        metrics.euclidean_distances(X[:10], Y[:, :5])
+    # rbf_kernel / pairwise_kernels
+    K = metrics.rbf_kernel(Xc, Y).compute()
+    np.testing.assert_allclose(K, skp.rbf_kernel(X, Y), rtol=1e-4, atol=1e-6)
+    K2 = metrics.pairwise_kernels(X[:40], Y[:30], metric="rbf", gamma=0.3).compute()
+    np.testing.assert_allclose(K2, skp.rbf_kernel(X[:40], Y[:30], gamma=0.3), rtol=1e-4, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        metrics.pairwise_kernels(X[:4], Y[:4], metric="polynomial")
+    with pytest.raises(ValueError):
+        metrics.pairwise_kernels(X[:4], Y[:4], metric="nope")
+    with pytest.raises(TypeError):
+        metrics.pairwise_distances(X[:4], type("A", (), {"__module__": "dask.array.core"})())
+    with pytest.raises(NotImplementedError):
+        metrics.pairwise_distances(X[:4], Y[:4], metric="cosine")
