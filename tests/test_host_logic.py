@@ -310,3 +310,24 @@ def test_metrics_operators_host_logic(monkeypatch):
         metrics.pairwise_distances(X[:4], type("A", (), {"__module__": "dask.array.core"})())
     with pytest.raises(NotImplementedError):
         metrics.pairwise_distances(X[:4], Y[:4], metric="cosine")
+
+
+def test_p2p_mailbox_sizing_and_argument_checks():
+    """Host-side contract of the peer-memory collective (include/bkm_b200.h): mailbox size = 1 KB header + 2 parities x
+    world slots of max_elems float64; argument errors are return codes (no device needed)."""
+    import ctypes
+    from dask_ml_b200 import _lib
+
+    lib = _lib.load()
+    nb = ctypes.c_size_t(0)
+    assert lib.bkm_p2p_mailbox_bytes(8, 1 << 16, ctypes.byref(nb)) == 0
+    assert nb.value == 1024 + 2 * 8 * (1 << 16) * 8
+    assert lib.bkm_p2p_mailbox_bytes(1, 1, ctypes.byref(nb)) == 0 and nb.value == 1024 + 16
+    for world, m in ((0, 16), (65, 16), (2, 0)):
+        assert lib.bkm_p2p_mailbox_bytes(world, m, ctypes.byref(nb)) < 0
+    # n > max_elems, bad rank, null pointers: rejected before anything touches a device
+    dummy = ctypes.c_void_p(16)
+    assert lib.bkm_allreduce_p2p(dummy, 10, dummy, 0, 2, 5, 1, None) < 0
+    assert lib.bkm_allreduce_p2p(dummy, 4, dummy, 2, 2, 5, 1, None) < 0
+    assert lib.bkm_allreduce_p2p(None, 4, dummy, 0, 2, 5, 1, None) < 0
+    assert lib.bkm_allreduce_p2p(dummy, 0, dummy, 0, 2, 5, 1, None) == 0          # empty payload: nothing to do
